@@ -1,0 +1,99 @@
+/*
+ * seedstory_b200 — C-ABI of the B200-native SEED-Story inference hot path.
+ *
+ * The reference (TencentARC/SEED-Story) has no FFI of its own: its "plugin API" is hydra `_target_`
+ * paths plus duck-typed attribute access.  The host-side mirror of that API lives in
+ * seed-story_b200/src/… (Python, same module paths and signatures); everything arithmetic behind it is
+ * reached through the entry points declared here.  Each entry point cites the reference code whose
+ * arithmetic it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - every function returns 0 on success; on failure it returns non-zero and ss_last_error() holds a
+ *     thread-local message.  There is no CPU fallback anywhere.
+ *   - all data pointers are DEVICE pointers (plain `void*` / `int*`), sizes are element counts,
+ *     `stream` is a cudaStream_t passed as `void*` (NULL = default stream).  No torch types.
+ *   - dtype tags: 0 = fp16, 1 = bf16.  Matrices are row-major; `ld*` are row pitches in elements.
+ *   - KV cache pages hold 64 tokens: one page of one layer is [heads][64][head_dim] 16-bit values.
+ */
+#ifndef SEEDSTORY_B200_H
+#define SEEDSTORY_B200_H
+
+#ifdef __cplusplus
+#define SS_EXPORT extern "C"
+#else
+#define SS_EXPORT
+#endif
+
+#define SS_DTYPE_F16 0
+#define SS_DTYPE_BF16 1
+
+#define SS_KV_PAGE_TOKENS 64
+
+/* ---- library ------------------------------------------------------------------------------- */
+SS_EXPORT const char* ss_last_error(void);
+SS_EXPORT int ss_version(void);
+/* fails unless an sm_100 device is current; writes its SM count */
+SS_EXPORT int ss_require_device(int* sm_count_out);
+SS_EXPORT int ss_stream_sync(void* stream);
+
+/* ---- row normalisations --------------------------------------------------------------------- */
+/* LlamaRMSNorm.forward — src/models_clm/modeling_llama_xformer.py:107-115 (fp32 variance, x*rsqrt
+ * rounded to fp16, then fp16 weight multiply). */
+SS_EXPORT int ss_rmsnorm_f16(const void* x, int ldx, const void* weight, void* y, int ldy, int rows, int K, float eps,
+                             void* stream);
+/* nn.LayerNorm as used at src/models/qwen_visual.py:143-147,353-354 and src/models_ipa/resampler.py:40-41;
+ * optional second output y2 = LN(x) + add[row % add_rows] (the positional-embedding adds of
+ * Resampler.forward, qwen_visual.py:146-148). */
+SS_EXPORT int ss_layernorm(int dtype, const void* x, int ldx, const void* gamma, const void* beta, void* y, int ldy,
+                           int rows, int K, float eps, const void* add, int add_rows, void* y2, int ldy2,
+                           void* stream);
+/* F.normalize(x) over dim=1 of [B,T,C] — src/models_ipa/resampler.py:269 */
+SS_EXPORT int ss_l2norm_tokens_f16(const void* x, void* y, int B, int T, int C, void* stream);
+
+/* ---- Llama decode step (batch <= 8) ---------------------------------------------------------- */
+/* y[b,n] = sum_k x[b,k] W[n,k] for the q/k/v/o/gate/up/down/lm_head projections of a decode step —
+ * modeling_llama_xformer.py:228-230, 296, 191, 759.  epilogue: 0 none, 1 y = residual + y (fp16 add,
+ * :353/:359), 2 SwiGLU on interleaved (gate_j, up_j) row pairs -> y[b, j], j < N/2 (:191). */
+SS_EXPORT int ss_skinny_gemm_f16(const void* x, int ldx, const void* W, void* y, int ldy, int B, int N, int K,
+                                 int epilogue, const void* residual, int ldr, void* stream);
+/* apply_rotary_pos_emb (:165-173) on q and k, then append k (post-RoPE) and v to the paged cache
+ * (replaces the torch.cat at :241-242).  qkv rows are [q | k | v], each H*D wide. */
+SS_EXPORT int ss_rope_kv_append_f16(const void* qkv, int ld_qkv, void* q_out, void* kcache, void* vcache,
+                                    const int* tok_seq, const int* tok_pos, const int* tok_slot, int ntok,
+                                    const int* page_table, int max_pages, const void* cos_table,
+                                    const void* sin_table, int H, int D, void* stream);
+/* xops.memory_efficient_attention(q,k,v, LowerTriangularFromBottomRightMask) for q_len == 1 (:289-295)
+ * over the pages retained in page_table (window + attention-sink pages). workspace: B*H*splits*(D+2) floats. */
+SS_EXPORT int ss_attn_decode_paged_f16(const void* q, const void* kcache, const void* vcache, const int* seq_lens,
+                                       const int* page_table, int max_pages, void* out, float* workspace, int B, int H,
+                                       int D, int splits, float scale, void* stream);
+/* AutoImageTokenGenerationProcessor.__call__ (src/models_clm/generation.py:19-31) + greedy argmax.
+ * img_ids = [BOI, IMG_0..IMG_{n-3}, EOI]; NULL disables the processor. Logits are edited in place. */
+SS_EXPORT int ss_logits_process_argmax_f16(void* logits, int ld, int V, const int* last_ids, const int* img_ids,
+                                           int n_img_ids, int* next_ids, int B, void* stream);
+/* embed_tokens lookup — modeling_llama_xformer.py:580-581 / models.py:127 */
+SS_EXPORT int ss_gather_rows_16b(const void* table, const int* ids, void* out, int ld_out, int ntok, int width,
+                                 void* stream);
+/* greedy-loop bookkeeping on the device (append id, advance position/slot/length, EOS -> done) —
+ * restates the sequence/position updates of HF greedy_search + prepare_inputs_for_generation (:827-844) */
+SS_EXPORT int ss_decode_advance(const int* next_ids, int* cur_ids, int* tok_pos, int* tok_slot, int* seq_lens,
+                                int* out_ids, int out_cap, int* n_out, int* done, int eos_id, int B, void* stream);
+
+/* ---- dense contractions on tcgen05 ------------------------------------------------------------ */
+/* C[M,N] = epi(alpha * A[M,K] B[N,K]^T): every nn.Linear on the prefill / ViT / resampler / UNet /
+ * VAE paths (e.g. qwen_visual.py:191,233,258-260; resampler.py:58-76; modeling_llama_xformer.py:228-230).
+ * epilogue order: +bias[N] -> round -> +bias2[row / rows_per_group, N] -> round -> act (1 gelu-erf,
+ * 2 silu) -> round -> +residual -> round.  glu: 1 = first*gelu(second) (diffusers GEGLU), 2 =
+ * silu(first)*second (LlamaMLP, :191) over interleaved column pairs, output width N/2.
+ * force_bn: 0 = auto, else 64/128/256 (N tile). */
+SS_EXPORT int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N,
+                         int K, const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr,
+                         int act, int glu, float alpha, int force_bn, void* stream);
+/* 3x3 / stride 1 / pad 1 convolution on NHWC activations as an implicit GEMM (diffusers ResnetBlock2D
+ * conv1/conv2, Up/Downsample convs, VAE decoder convs — SURVEY.md Appendix C).  w is [Cout, 9*Cin] with
+ * k = (ky*3+kx)*Cin + c.  bias2 is the per-image time-embedding row [Nimg, Cout]. */
+SS_EXPORT int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin,
+                              int Cout, const void* bias, const void* bias2, const void* residual, int act,
+                              int force_bn, void* stream);
+
+#endif /* SEEDSTORY_B200_H */

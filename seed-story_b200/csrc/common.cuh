@@ -1,0 +1,121 @@
+// Shared device/host helpers for the seedstory_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+// ---------------------------------------------------------------------------------------------
+// Error convention of the C-ABI: every entry point returns 0 on success, non-zero on failure and
+// leaves a thread-local message readable through ss_last_error().
+// ---------------------------------------------------------------------------------------------
+namespace ss {
+void set_error(const std::string& msg);
+int fail(const char* file, int line, const std::string& msg);
+}  // namespace ss
+
+#define SS_FAIL(msg) return ss::fail(__FILE__, __LINE__, (msg))
+#define SS_REQUIRE(cond, msg)                         \
+  do {                                                \
+    if (!(cond)) return ss::fail(__FILE__, __LINE__, std::string("requirement failed: " #cond " — ") + (msg)); \
+  } while (0)
+#define SS_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return ss::fail(__FILE__, __LINE__, std::string(#expr ": ") + cudaGetErrorString(_e)); \
+  } while (0)
+#define SS_LAUNCH_CHECK() SS_CUDA(cudaGetLastError())
+
+#define SS_API extern "C" __attribute__((visibility("default")))
+
+// ---------------------------------------------------------------------------------------------
+// dtype tags used across the C-ABI (matches include/seedstory_b200.h)
+// ---------------------------------------------------------------------------------------------
+enum { SS_F16 = 0, SS_BF16 = 1, SS_F32 = 2 };
+
+template <typename T> struct ss_num;
+template <> struct ss_num<__half> {
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+template <> struct ss_num<__nv_bfloat16> {
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// 16-byte vector of 8 x 16-bit values
+struct __align__(16) vec8 {
+  uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ vec8 ld_stream16(const void* p) {  // weights: read once, keep out of L1
+  vec8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ vec8 ld_cached16(const void* p) {
+  vec8 r;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st16(void* p, const vec8& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ void unpack8(const vec8& v, float* f) {
+  const T* h = reinterpret_cast<const T*>(&v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = ss_num<T>::to_f(h[i]);
+}
+template <typename T>
+__device__ __forceinline__ vec8 pack8(const float* f) {
+  vec8 v;
+  T* h = reinterpret_cast<T*>(&v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = ss_num<T>::from_f(f[i]);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum over up to 1024 threads; `red` must hold 32 floats of shared memory
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : -INFINITY;
+  t = warp_max(t);
+  return t;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

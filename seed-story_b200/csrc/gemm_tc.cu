@@ -1,0 +1,453 @@
+// Dense contraction on the 5th-gen tensor cores:  C[M,N] = epilogue(A[M,K] · B[N,K]^T)
+//   * operands: 16-bit (fp16 or bf16), both K-major (x[M,K] and nn.Linear weight [N,K] as stored)
+//   * TMA (cp.async.bulk.tensor, 128B swizzle) stages 128 x 64 / BN x 64 tiles into a shared-memory ring
+//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator
+//   * four epilogue warps read TMEM with tcgen05.ld and apply bias / activation / GLU / residual
+//   * the same kernel is an implicit-GEMM 3x3 convolution (NHWC): the A tile for filter tap (ky,kx)
+//     is a 4-D TMA box shifted by (ky-1, kx-1); out-of-bounds pixels are zero-filled by the TMA unit,
+//     which IS the conv padding.
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
+#include <cstring>
+#include <mutex>
+#include <type_traits>
+#include <unordered_map>
+#include <vector>
+
+#include "tc.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 16-bit = 128 bytes = one swizzle row
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  void* out;
+  int ldo;
+  const void* bias;      // [N] or null
+  const void* bias2;     // [groups, N] or null; group = row / rows_per_group
+  int rows_per_group;
+  const void* residual;  // [M, ldr] or null
+  int ldr;
+  int act;  // 0 none, 1 gelu(erf), 2 silu
+  int glu;  // 0 none, 1 first*gelu(second), 2 silu(first)*second   (column pairs interleaved)
+  float alpha;
+  int M, N, K;
+  // conv mode
+  int H, W, Cin, bw, bh, tiles_x, tiles_y;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <typename T>
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == 1) return gelu_erf(v);
+  if (act == 2) return v / (1.f + expf(-v));
+  return v;
+}
+
+template <typename T, int BN, bool CONV>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const GemmParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::STAGES * L::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + L::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + L::STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+
+  // tile coordinates
+  int m0 = 0, img = 0, y0 = 0, x0 = 0;
+  if (CONV) {
+    int t = blockIdx.y;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    img = t / p.tiles_y;
+    y0 = ty * p.bh;
+    x0 = tx * p.bw;
+  } else {
+    m0 = blockIdx.y * BM;
+  }
+  const int kchunks = CONV ? (p.Cin / BK) : ((p.K + BK - 1) / BK);
+  const int num_kb = CONV ? 9 * kchunks : kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < L::STAGES; ++s) {
+        tc::mbar_init(&full_bar[s], 1);
+        tc::mbar_init(&empty_bar[s], 1);
+      }
+      tc::mbar_init(tmem_full_bar, 1);
+      tc::fence_barrier_init();
+    }
+    __syncwarp();
+    tc::tmem_alloc(tmem_ptr_smem, BN < 32 ? 32 : BN);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % L::STAGES;
+        const uint32_t ph = (kb / L::STAGES) & 1;
+        tc::mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        tc::mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        if (CONV) {
+          const int tap = kb / kchunks, c0 = (kb % kchunks) * BK;
+          const int ky = tap / 3, kx = tap % 3;
+          tc::tma_load_4d(sa, &tmA, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, img);
+          tc::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.Cin + c0, n0);
+        } else {
+          tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+          tc::tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(sizeof(T) == 2 && !std::is_same<T, __half>::value, BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % L::STAGES;
+        const uint32_t ph = (kb / L::STAGES) & 1;
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::fence_after_sync();
+        const uint32_t sa = tc::smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+        const uint64_t da = tc::make_desc_sw128(sa);
+        const uint64_t db = tc::make_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
+          tc::mma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        tc::mma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+      }
+      tc::mma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::fence_after_sync();
+
+    long long m;  // output row
+    bool row_ok;
+    if (CONV) {
+      const int yy = y0 + r / p.bw, xx = x0 + r % p.bw;
+      m = ((long long)img * p.H + yy) * p.W + xx;
+      row_ok = (yy < p.H) && (xx < p.W);
+    } else {
+      m = m0 + r;
+      row_ok = m < p.M;
+    }
+    T* out_row = reinterpret_cast<T*>(p.out) + m * p.ldo;
+    const T* res_row = p.residual ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
+    const T* b2_row =
+        p.bias2 ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.N : nullptr;
+
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t raw[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+      tc::tmem_ld_wait();
+      const int col0 = n0 + c;
+      if (!row_ok || col0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+      // columns are handled in groups of 8 (16-byte vectors); N % 8 == 0 is required by the host
+#pragma unroll
+      for (int gI = 0; gI < 4; ++gI) {
+        const int col = col0 + gI * 8;
+        if (col >= p.N) break;
+        float* vv = v + gI * 8;
+        if (p.bias) {
+          float bf[8];
+          unpack8<T>(ld_cached16(reinterpret_cast<const T*>(p.bias) + col), bf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] += bf[i];
+        }
+        // round to storage precision after every reference-visible op
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i]));
+        if (b2_row) {
+          float bf[8];
+          unpack8<T>(ld_cached16(b2_row + col), bf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
+        }
+        if (p.glu == 0) {
+          if (p.act) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(act_apply<T>(vv[i], p.act)));
+          }
+          if (res_row) {
+            float rf[8];
+            unpack8<T>(ld_cached16(res_row + col), rf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] += rf[i];
+          }
+          st16(out_row + col, pack8<T>(vv));
+        } else {
+          // interleaved pairs (first, second) -> 4 outputs per 8 columns
+          T o4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = vv[2 * i], b = vv[2 * i + 1];
+            float o;
+            if (p.glu == 1)
+              o = a * ss_num<T>::to_f(ss_num<T>::from_f(gelu_erf(b)));
+            else
+              o = ss_num<T>::to_f(ss_num<T>::from_f(a / (1.f + expf(-a)))) * b;
+            o4[i] = ss_num<T>::from_f(o);
+          }
+          *reinterpret_cast<uint2*>(out_row + (col >> 1)) = *reinterpret_cast<const uint2*>(o4);
+        }
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point resolved at run time) + cache
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int dtype, rank;
+  uint64_t dims[4];
+  uint64_t strides[3];
+  uint32_t box[4];
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return h;
+  }
+};
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+std::mutex g_tmap_mu;
+
+// dims/strides innermost first; strides in bytes for dims 1..rank-1
+int get_tmap(CUtensorMap* out, const void* ptr, int dtype, int rank, const uint64_t* dims, const uint64_t* strides,
+             const uint32_t* box) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr;
+  key.dtype = dtype;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i + 1 < rank) key.strides[i] = strides[i];
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  SS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides[i];
+  }
+  SS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  for (int i = 0; i + 1 < rank; ++i) SS_REQUIRE(strides[i] % 16 == 0, "TMA strides must be multiples of 16 bytes");
+  CUtensorMap tm;
+  CUresult r = fn(&tm, dtype == SS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                  const_cast<void*>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) SS_FAIL("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmaps.size() > 65536) g_tmaps.clear();
+    g_tmaps[key] = tm;
+  }
+  *out = tm;
+  return 0;
+}
+
+template <typename T, int BN, bool CONV>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t s) {
+  using L = SmemLayout<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  gemm_tc_kernel<T, BN, CONV><<<grid, GEMM_THREADS, L::TOTAL, s>>>(ta, tb, p);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool CONV>
+int dispatch(int dtype, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
+             cudaStream_t s) {
+  if (dtype == SS_F16) {
+    if (bn == 64) return launch<__half, 64, CONV>(ta, tb, p, grid, s);
+    if (bn == 128) return launch<__half, 128, CONV>(ta, tb, p, grid, s);
+    return launch<__half, 256, CONV>(ta, tb, p, grid, s);
+  } else {
+    if (bn == 64) return launch<__nv_bfloat16, 64, CONV>(ta, tb, p, grid, s);
+    if (bn == 128) return launch<__nv_bfloat16, 128, CONV>(ta, tb, p, grid, s);
+    return launch<__nv_bfloat16, 256, CONV>(ta, tb, p, grid, s);
+  }
+}
+
+int pick_bn(long long m_tiles, int N, int force_bn) {
+  if (force_bn == 64 || force_bn == 128 || force_bn == 256) return force_bn;
+  if (N <= 64) return 64;
+  const long long t256 = m_tiles * ((N + 255) / 256), t128 = m_tiles * ((N + 127) / 128);
+  if (N >= 256 && t256 >= 2 * 148) return 256;
+  if (t128 >= 148) return 128;
+  return 64;
+}
+
+}  // namespace
+
+// C[M,N] = epi(alpha * A[M,K] B[N,K]^T); see include/seedstory_b200.h for the argument contract.
+SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                      const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr, int act,
+                      int glu, float alpha, int force_bn, void* stream) {
+  SS_REQUIRE(dtype == SS_F16 || dtype == SS_BF16, "dtype must be f16 or bf16");
+  SS_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
+  SS_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "N, K, lda, ldb, ldc % 8");
+  SS_REQUIRE(glu == 0 || (act == 0 && residual == nullptr), "GLU epilogue excludes act/residual");
+  SS_REQUIRE(bias2 == nullptr || rows_per_group > 0, "bias2 needs rows_per_group");
+  const long long m_tiles = (M + BM - 1) / BM;
+  const int bn = pick_bn(m_tiles, N, force_bn);
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {BK, BM};
+    if (int e = get_tmap(&ta, A, dtype, 2, dims, str, box)) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)ldb * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    if (int e = get_tmap(&tb, B, dtype, 2, dims, str, box)) return e;
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = C;
+  p.ldo = ldc;
+  p.bias = bias;
+  p.bias2 = bias2;
+  p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  p.residual = residual;
+  p.ldr = ldr;
+  p.act = act;
+  p.glu = glu;
+  p.alpha = alpha;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  dim3 grid((N + bn - 1) / bn, (unsigned)m_tiles);
+  return dispatch<false>(dtype, bn, ta, tb, p, grid, (cudaStream_t)stream);
+}
+
+// 3x3 stride-1 pad-1 convolution, NHWC activations [Nimg,H,W,Cin], weights [Cout, 9*Cin] with
+// k = (ky*3+kx)*Cin + c, output NHWC [Nimg,H,W,Cout].
+SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout,
+                           const void* bias, const void* bias2 /*[Nimg,Cout]*/, const void* residual, int act,
+                           int force_bn, void* stream) {
+  SS_REQUIRE(dtype == SS_F16 || dtype == SS_BF16, "dtype must be f16 or bf16");
+  SS_REQUIRE(Cin % BK == 0, "Cin must be a multiple of 64 for the tensor-core conv");
+  SS_REQUIRE(Cout % 8 == 0, "Cout must be a multiple of 8");
+  int bw = W >= 128 ? 128 : W, bh = BM / bw;
+  SS_REQUIRE(bw * bh == BM && W % bw == 0 && H % bh == 0, "image must tile into 128-pixel boxes");
+  const long long m_tiles = (long long)Nimg * (H / bh) * (W / bw);
+  const int bn = pick_bn(m_tiles, Cout, force_bn);
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {BK, (uint32_t)bw, (uint32_t)bh, 1};
+    if (int e = get_tmap(&ta, x, dtype, 4, dims, str, box)) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout}, str[1] = {(uint64_t)9 * Cin * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    if (int e = get_tmap(&tb, w, dtype, 2, dims, str, box)) return e;
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = y;
+  p.ldo = Cout;
+  p.bias = bias;
+  p.bias2 = bias2;
+  p.rows_per_group = H * W;
+  p.residual = residual;
+  p.ldr = Cout;
+  p.act = act;
+  p.alpha = 1.f;
+  p.M = Nimg * H * W;
+  p.N = Cout;
+  p.K = 9 * Cin;
+  p.H = H;
+  p.W = W;
+  p.Cin = Cin;
+  p.bw = bw;
+  p.bh = bh;
+  p.tiles_x = W / bw;
+  p.tiles_y = H / bh;
+  dim3 grid((Cout + bn - 1) / bn, (unsigned)m_tiles);
+  return dispatch<true>(dtype, bn, ta, tb, p, grid, (cudaStream_t)stream);
+}

@@ -1,0 +1,465 @@
+// Llama decode-step kernels (HBM-bound path, batch <= 8 sequences per rank):
+//   * skinny GEMM  y[b, n] = sum_k x[b, k] W[n, k]      (weight-streaming, fused epilogues)
+//   * RoPE + paged KV append                            (reference: modeling_llama_xformer.py:165-173, 236-244)
+//   * paged single-query attention, split over KV pages (reference: :282-295, bottom-right causal mask
+//                                                        degenerates to "see every cached token")
+//   * image-token logits processor + greedy argmax      (reference: src/models_clm/generation.py:19-31)
+//   * token-embedding gather, decode-state advance
+//
+// The skinny GEMM streams W once with 16-byte no-allocate loads and uses mma.sync.m16n8k16 purely as
+// a convenient 16x8 dot-product engine (N = 8 batch columns); it is bandwidth-bound by construction.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// skinny GEMM
+// ---------------------------------------------------------------------------------------------
+enum { EPI_NONE = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2 };
+
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int SG_WARPS = 8;
+constexpr int SG_UNROLL = 4;
+
+// One CTA = one 16-row tile of W; the 8 warps interleave over 32-wide k-blocks and their partial
+// 16x8 accumulators are reduced through shared memory.
+template <int EPI>
+__global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half* __restrict__ x, int ldx,
+                                                                    const __half* __restrict__ W,
+                                                                    __half* __restrict__ y, int ldy, int B, int N,
+                                                                    int K, const __half* __restrict__ res, int ldr) {
+  __shared__ float part[SG_WARPS][16][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = blockIdx.x * 16;
+  const int r_lo = min(row0 + g, N - 1), r_hi = min(row0 + g + 8, N - 1);  // clamp: tail rows are recomputed, not stored
+  const __half* w_lo = W + (size_t)r_lo * K + t * 8;
+  const __half* w_hi = W + (size_t)r_hi * K + t * 8;
+  const __half* xg = x + (size_t)min(g, B - 1) * ldx + t * 8;
+  const bool xvalid = g < B;
+  const int nkb = K >> 5;
+
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  int kb = warp;
+  for (; kb + (SG_UNROLL - 1) * SG_WARPS < nkb; kb += SG_UNROLL * SG_WARPS) {
+    vec8 a_lo[SG_UNROLL], a_hi[SG_UNROLL], xb[SG_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SG_UNROLL; ++u) {
+      const int off = (kb + u * SG_WARPS) << 5;
+      a_lo[u] = ld_stream16(w_lo + off);
+      a_hi[u] = ld_stream16(w_hi + off);
+    }
+#pragma unroll
+    for (int u = 0; u < SG_UNROLL; ++u) {
+      const int off = (kb + u * SG_WARPS) << 5;
+      xb[u] = xvalid ? ld_cached16(xg + off) : vec8{0u, 0u, 0u, 0u};
+    }
+#pragma unroll
+    for (int u = 0; u < SG_UNROLL; ++u) {
+      mma16816(c, a_lo[u].x, a_hi[u].x, a_lo[u].y, a_hi[u].y, xb[u].x, xb[u].y);
+      mma16816(c, a_lo[u].z, a_hi[u].z, a_lo[u].w, a_hi[u].w, xb[u].z, xb[u].w);
+    }
+  }
+  for (; kb < nkb; kb += SG_WARPS) {
+    const int off = kb << 5;
+    const vec8 a_lo = ld_stream16(w_lo + off), a_hi = ld_stream16(w_hi + off);
+    const vec8 xb = xvalid ? ld_cached16(xg + off) : vec8{0u, 0u, 0u, 0u};
+    mma16816(c, a_lo.x, a_hi.x, a_lo.y, a_hi.y, xb.x, xb.y);
+    mma16816(c, a_lo.z, a_hi.z, a_lo.w, a_hi.w, xb.z, xb.w);
+  }
+  // C fragment: c0,c1 -> (row g, col 2t,2t+1); c2,c3 -> (row g+8, col 2t,2t+1); col = batch index
+  part[warp][g][2 * t] = c[0];
+  part[warp][g][2 * t + 1] = c[1];
+  part[warp][g + 8][2 * t] = c[2];
+  part[warp][g + 8][2 * t + 1] = c[3];
+  __syncthreads();
+
+  if (EPI == EPI_SWIGLU) {
+    // tile rows (2j, 2j+1) are (gate_j, up_j): the host interleaves gate/up rows pairwise, the same
+    // packing the tensor-core GEMM's GLU epilogue consumes
+    if (threadIdx.x < 64) {
+      const int r = threadIdx.x >> 3, n = threadIdx.x & 7;
+      float gate = 0.f, up = 0.f;
+#pragma unroll
+      for (int w = 0; w < SG_WARPS; ++w) {
+        gate += part[w][2 * r][n];
+        up += part[w][2 * r + 1][n];
+      }
+      const int out_col = blockIdx.x * 8 + r;
+      if (n < B && out_col < (N >> 1)) {
+        const __half gh = __float2half_rn(gate);
+        const float gf = __half2float(gh);
+        const __half act = __float2half_rn(gf / (1.f + expf(-gf)));  // silu evaluated in fp32, rounded (torch half kernel)
+        y[(size_t)n * ldy + out_col] = __hmul(act, __float2half_rn(up));
+      }
+    }
+  } else {
+    if (threadIdx.x < 128) {
+      const int r = threadIdx.x >> 3, n = threadIdx.x & 7;
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < SG_WARPS; ++w) acc += part[w][r][n];
+      const int row = row0 + r;
+      if (n < B && row < N) {
+        __half o = __float2half_rn(acc);
+        if (EPI == EPI_RESIDUAL) o = __float2half_rn(__half2float(res[(size_t)n * ldr + row]) + __half2float(o));
+        y[(size_t)n * ldy + row] = o;
+      }
+    }
+  }
+}
+
+SS_API int ss_skinny_gemm_f16(const void* x, int ldx, const void* W, void* y, int ldy, int B, int N, int K,
+                              int epilogue, const void* residual, int ldr, void* stream) {
+  SS_REQUIRE(B >= 1 && B <= 8, "skinny GEMM handles 1..8 rows");
+  SS_REQUIRE(K % 32 == 0 && ldx % 8 == 0, "K must be a multiple of 32, ldx of 8");
+  SS_REQUIRE(epilogue != EPI_SWIGLU || N % 16 == 0, "SwiGLU needs N % 16 == 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = ceil_div(N, 16);
+  const __half *xp = (const __half*)x, *Wp = (const __half*)W, *rp = (const __half*)residual;
+  __half* yp = (__half*)y;
+  switch (epilogue) {
+    case EPI_NONE:
+      skinny_gemm_kernel<EPI_NONE><<<grid, SG_WARPS * 32, 0, s>>>(xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr);
+      break;
+    case EPI_RESIDUAL:
+      SS_REQUIRE(residual != nullptr, "residual epilogue needs a residual pointer");
+      skinny_gemm_kernel<EPI_RESIDUAL><<<grid, SG_WARPS * 32, 0, s>>>(xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr);
+      break;
+    case EPI_SWIGLU:
+      skinny_gemm_kernel<EPI_SWIGLU><<<grid, SG_WARPS * 32, 0, s>>>(xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr);
+      break;
+    default:
+      SS_FAIL("unknown epilogue");
+  }
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoPE + paged KV append.  One CTA per token, 128 threads... each thread owns pairs (d, d+64) of
+// one head at a time.  All arithmetic in fp16 exactly as the reference: q*cos + rotate_half(q)*sin
+// with fp16 tables (two fp16 products, one fp16 add).
+//   qkv   [ntok, 3*H*D]  (q | k | v)
+//   q_out [ntok, H*D]
+//   K/V cache pages: [page][H][PAGE][D]
+// ---------------------------------------------------------------------------------------------
+constexpr int KV_PAGE = 64;
+
+__device__ __forceinline__ __half hadd_t(__half a, __half b) {  // torch's half add: fp32 add, one rounding
+  return __float2half_rn(__half2float(a) + __half2float(b));
+}
+
+__global__ void __launch_bounds__(256) rope_append_kernel(const __half* __restrict__ qkv, int ld_qkv,
+                                                          __half* __restrict__ q_out, __half* __restrict__ kcache,
+                                                          __half* __restrict__ vcache, const int* __restrict__ tok_seq,
+                                                          const int* __restrict__ tok_pos,
+                                                          const int* __restrict__ tok_slot,
+                                                          const int* __restrict__ page_table, int max_pages,
+                                                          const __half* __restrict__ cos_t,
+                                                          const __half* __restrict__ sin_t, int H, int D) {
+  const int tok = blockIdx.x;
+  const int seq = tok_seq[tok], pos = tok_pos[tok], slot = tok_slot[tok];
+  const int page = page_table[(size_t)seq * max_pages + slot / KV_PAGE];
+  const int in_page = slot % KV_PAGE;
+  const int half_d = D >> 1;
+  const __half* row = qkv + (size_t)tok * ld_qkv;
+  const __half* cr = cos_t + (size_t)pos * D;
+  const __half* sr = sin_t + (size_t)pos * D;
+  const int HD = H * D;
+  for (int i = threadIdx.x; i < H * half_d; i += blockDim.x) {
+    const int h = i / half_d, d = i % half_d;
+    const __half c0 = cr[d], c1 = cr[d + half_d], s0 = sr[d], s1 = sr[d + half_d];
+    const size_t dst = (((size_t)page * H + h) * KV_PAGE + in_page) * D;
+    {  // q
+      const __half x0 = row[h * D + d], x1 = row[h * D + d + half_d];
+      q_out[(size_t)tok * HD + h * D + d] = hadd_t(__hmul(x0, c0), __hmul(__hneg(x1), s0));
+      q_out[(size_t)tok * HD + h * D + d + half_d] = hadd_t(__hmul(x1, c1), __hmul(x0, s1));
+    }
+    {  // k
+      const __half x0 = row[HD + h * D + d], x1 = row[HD + h * D + d + half_d];
+      kcache[dst + d] = hadd_t(__hmul(x0, c0), __hmul(__hneg(x1), s0));
+      kcache[dst + d + half_d] = hadd_t(__hmul(x1, c1), __hmul(x0, s1));
+    }
+    {  // v (raw)
+      vcache[dst + d] = row[2 * HD + h * D + d];
+      vcache[dst + d + half_d] = row[2 * HD + h * D + d + half_d];
+    }
+  }
+}
+
+SS_API int ss_rope_kv_append_f16(const void* qkv, int ld_qkv, void* q_out, void* kcache, void* vcache,
+                                 const int* tok_seq, const int* tok_pos, const int* tok_slot, int ntok,
+                                 const int* page_table, int max_pages, const void* cos_table, const void* sin_table,
+                                 int H, int D, void* stream) {
+  SS_REQUIRE(D % 2 == 0, "head dim must be even");
+  if (ntok == 0) return 0;
+  rope_append_kernel<<<ntok, 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)qkv, ld_qkv, (__half*)q_out, (__half*)kcache, (__half*)vcache, tok_seq, tok_pos, tok_slot,
+      page_table, max_pages, (const __half*)cos_table, (const __half*)sin_table, H, D);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Paged decode attention, D = 128, one query token per sequence.
+// grid (H, B, S): split s of sequence b handles pages [s*pps, (s+1)*pps) where pps is derived from
+// the device-side sequence length, so the launch is CUDA-graph replayable while lengths grow.
+// ---------------------------------------------------------------------------------------------
+constexpr int AD_THREADS = 128;
+constexpr int AD_MAX_CHUNK = 1024;  // tokens per split upper bound (16 pages)
+
+__global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
+    const __half* __restrict__ q, const __half* __restrict__ kcache, const __half* __restrict__ vcache,
+    const int* __restrict__ seq_lens, const int* __restrict__ page_table, int max_pages, float* __restrict__ part,
+    int H, int S, float scale) {
+  constexpr int D = 128;
+  __shared__ float sc[AD_MAX_CHUNK];
+  __shared__ float red[32];
+  __shared__ __align__(16) __half qs[D];
+  const int h = blockIdx.x, b = blockIdx.y, s = blockIdx.z;
+  const int n = seq_lens[b];
+  const int npages = (n + KV_PAGE - 1) / KV_PAGE;
+  const int pps = (npages + S - 1) / S;  // pages per split
+  const int p0 = s * pps, p1 = min(npages, p0 + pps);
+  float* out = part + (((size_t)b * H + h) * S + s) * (D + 2);
+  if (p0 >= p1) {
+    if (threadIdx.x == 0) {
+      out[D] = -INFINITY;
+      out[D + 1] = 0.f;
+    }
+    out[threadIdx.x] = 0.f;
+    return;
+  }
+  const int t0 = p0 * KV_PAGE, t1 = min(n, p1 * KV_PAGE), cnt = t1 - t0;
+  if (threadIdx.x < D) qs[threadIdx.x] = q[((size_t)b * H + h) * D + threadIdx.x];
+  __syncthreads();
+
+  // phase 1: scores. 16 lanes x 16 bytes cover one 256-byte key row; a warp does 2 tokens per iteration.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane >> 4, l16 = lane & 15;
+  float qf[8];
+  unpack8<__half>(*reinterpret_cast<const vec8*>(qs + l16 * 8), qf);
+  const int* pt = page_table + (size_t)b * max_pages;
+  float lmax = -INFINITY;
+  for (int j = warp * 2 + sub; j < cnt; j += (AD_THREADS / 32) * 2) {
+    const int tok = t0 + j;
+    const int page = pt[tok / KV_PAGE];
+    const __half* kr = kcache + (((size_t)page * H + h) * KV_PAGE + (tok % KV_PAGE)) * D + l16 * 8;
+    float kf[8];
+    unpack8<__half>(ld_cached16(kr), kf);
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d += qf[i] * kf[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    d *= scale;
+    if (l16 == 0) sc[j] = d;
+    lmax = fmaxf(lmax, d);
+  }
+  const float m = block_max(lmax, red);
+  // phase 2: exponentials
+  float lsum = 0.f;
+  for (int j = threadIdx.x; j < cnt; j += AD_THREADS) {
+    const float e = __expf(sc[j] - m);
+    sc[j] = e;
+    lsum += e;
+  }
+  const float l = block_sum(lsum, red);
+  // phase 3: O = sum_j p_j V[j]; thread d owns output dim d (coalesced 256-byte value rows)
+  float acc = 0.f;
+  const int d = threadIdx.x;
+#pragma unroll 8
+  for (int j = 0; j < cnt; ++j) {
+    const int tok = t0 + j;
+    const int page = pt[tok / KV_PAGE];
+    acc += sc[j] * __half2float(vcache[(((size_t)page * H + h) * KV_PAGE + (tok % KV_PAGE)) * D + d]);
+  }
+  out[d] = acc;
+  if (threadIdx.x == 0) {
+    out[D] = m;
+    out[D + 1] = l;
+  }
+}
+
+__global__ void __launch_bounds__(128) attn_decode_combine_kernel(const float* __restrict__ part,
+                                                                  __half* __restrict__ out, int H, int S) {
+  constexpr int D = 128;
+  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const float* p = part + ((size_t)b * H + h) * S * (D + 2);
+  float m = -INFINITY;
+  for (int s = 0; s < S; ++s) m = fmaxf(m, p[s * (D + 2) + D]);
+  float num = 0.f, den = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float ms = p[s * (D + 2) + D];
+    if (ms == -INFINITY) continue;
+    const float w = __expf(ms - m);
+    num += w * p[s * (D + 2) + d];
+    den += w * p[s * (D + 2) + D + 1];
+  }
+  out[((size_t)b * H + h) * D + d] = __float2half_rn(num / den);
+}
+
+SS_API int ss_attn_decode_paged_f16(const void* q, const void* kcache, const void* vcache, const int* seq_lens,
+                                    const int* page_table, int max_pages, void* out, float* workspace, int B, int H,
+                                    int D, int splits, float scale, void* stream) {
+  SS_REQUIRE(D == 128, "decode attention is specialised for head_dim 128");
+  SS_REQUIRE(splits >= 1 && (max_pages + splits - 1) / splits * KV_PAGE <= AD_MAX_CHUNK,
+             "too few splits for max_pages (each split holds <= 1024 tokens)");
+  if (B == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  attn_decode_split_kernel<<<dim3(H, B, splits), AD_THREADS, 0, s>>>(
+      (const __half*)q, (const __half*)kcache, (const __half*)vcache, seq_lens, page_table, max_pages, workspace, H,
+      splits, scale);
+  SS_LAUNCH_CHECK();
+  attn_decode_combine_kernel<<<dim3(H, B), 128, 0, s>>>(workspace, (__half*)out, H, splits);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Image-token logits processor + greedy argmax (one CTA per sequence).
+// Semantics of AutoImageTokenGenerationProcessor (generation.py:19-31) followed by argmax:
+//   last id in img_ids[0 .. n-2]  -> scores[img_ids[idx+1]] = max(scores) + 10   (fp16 add)
+//   otherwise                     -> scores[img_ids[1 .. n-1]] = 0.0
+// then argmax with ties resolved to the lowest index.  The logits row is modified in place exactly
+// as the reference modifies `scores`.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) logits_argmax_kernel(__half* __restrict__ logits, int ld, int V,
+                                                             const int* __restrict__ last_ids,
+                                                             const int* __restrict__ img_ids, int n_img_ids,
+                                                             int* __restrict__ next_ids) {
+  __shared__ float red_v[32];
+  __shared__ int red_i[32];
+  __shared__ int forced_s;
+  const int b = blockIdx.x;
+  __half* row = logits + (size_t)b * ld;
+  if (threadIdx.x == 0) {
+    int forced = -1;
+    if (img_ids != nullptr) {
+      const int last = last_ids[b];
+      for (int i = 0; i + 1 < n_img_ids; ++i)
+        if (img_ids[i] == last) {
+          forced = img_ids[i + 1];
+          break;
+        }
+    }
+    forced_s = forced;
+  }
+  __syncthreads();
+  const int forced = forced_s;
+  if (img_ids != nullptr && forced < 0) {
+    if (threadIdx.x >= 1 && threadIdx.x < n_img_ids) row[img_ids[threadIdx.x]] = __float2half_rn(0.f);
+    __syncthreads();
+  }
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = __half2float(row[i]);
+    if (v > best || (v == best && i < besti)) {
+      best = v;
+      besti = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) {
+      best = ov;
+      besti = oi;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    red_v[wid] = best;
+    red_i[wid] = besti;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    best = red_v[lane];
+    besti = red_i[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ov > best || (ov == best && oi < besti)) {
+        best = ov;
+        besti = oi;
+      }
+    }
+    if (lane == 0) {
+      if (forced >= 0) {
+        row[forced] = __hadd(__float2half_rn(best), __float2half_rn(10.f));
+        next_ids[b] = forced;  // max+10 beats every other entry
+      } else {
+        next_ids[b] = besti;
+      }
+    }
+  }
+}
+
+SS_API int ss_logits_process_argmax_f16(void* logits, int ld, int V, const int* last_ids, const int* img_ids,
+                                        int n_img_ids, int* next_ids, int B, void* stream) {
+  SS_REQUIRE(n_img_ids <= 1024, "image-token list too long");
+  if (B == 0) return 0;
+  logits_argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((__half*)logits, ld, V, last_ids, img_ids, n_img_ids,
+                                                             next_ids);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Embedding gather (rows of 16-bit values) and decode-state advance.
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const uint16_t* __restrict__ table, const int* __restrict__ ids,
+                                   uint16_t* __restrict__ out, int ld_out, int width) {
+  const int tok = blockIdx.x;
+  const vec8* src = reinterpret_cast<const vec8*>(table + (size_t)ids[tok] * width);
+  vec8* dst = reinterpret_cast<vec8*>(out + (size_t)tok * ld_out);
+  for (int i = threadIdx.x; i < (width >> 3); i += blockDim.x) dst[i] = src[i];
+}
+
+SS_API int ss_gather_rows_16b(const void* table, const int* ids, void* out, int ld_out, int ntok, int width,
+                              void* stream) {
+  SS_REQUIRE(width % 8 == 0 && ld_out % 8 == 0, "row width must be a multiple of 8 elements");
+  if (ntok == 0) return 0;
+  gather_rows_kernel<<<ntok, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)table, ids, (uint16_t*)out, ld_out,
+                                                            width);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// After a decode step: last_id <- next_id; position, slot and length advance by one for live sequences;
+// the emitted id is appended to the per-sequence output ring and the final-norm hidden row is kept.
+__global__ void decode_advance_kernel(const int* __restrict__ next_ids, int* __restrict__ cur_ids,
+                                      int* __restrict__ tok_pos, int* __restrict__ tok_slot,
+                                      int* __restrict__ seq_lens, int* __restrict__ out_ids, int out_cap,
+                                      int* __restrict__ n_out, int* __restrict__ done, int eos_id, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (done[b]) return;
+  const int id = next_ids[b];
+  const int k = n_out[b];
+  if (k < out_cap) out_ids[(size_t)b * out_cap + k] = id;
+  n_out[b] = k + 1;
+  cur_ids[b] = id;
+  tok_pos[b] += 1;
+  tok_slot[b] += 1;
+  seq_lens[b] += 1;
+  if (id == eos_id) done[b] = 1;
+}
+
+SS_API int ss_decode_advance(const int* next_ids, int* cur_ids, int* tok_pos, int* tok_slot, int* seq_lens,
+                             int* out_ids, int out_cap, int* n_out, int* done, int eos_id, int B, void* stream) {
+  if (B == 0) return 0;
+  decode_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(next_ids, cur_ids, tok_pos, tok_slot, seq_lens, out_ids,
+                                                            out_cap, n_out, done, eos_id, B);
+  SS_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,161 @@
+"""Thin torch-tensor front end over the C-ABI (device pointers + current stream in, nothing else).
+
+torch is used here for device memory and streams only; every function launches hand-written sm_100a
+kernels from libseedstory_b200.so and raises if the library or a CUDA device is missing.
+"""
+import ctypes
+
+import torch
+
+from . import _capi
+
+F16, BF16 = 0, 1
+KV_PAGE = 64
+
+
+def _dt(t):
+    if t.dtype == torch.float16:
+        return F16
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"seedstory_b200 kernels take fp16/bf16 tensors, got {t.dtype}")
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _capi.SeedStoryError("seedstory_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def require_device():
+    n = ctypes.c_int(0)
+    _capi.call("ss_require_device", ctypes.byref(n))
+    return n.value
+
+
+def rmsnorm(x, weight, eps, out=None):
+    _req_cuda(x, weight)
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    out = torch.empty_like(x2) if out is None else out
+    _capi.call("ss_rmsnorm_f16", _p(x2), x2.stride(0), _p(weight), _p(out), out.stride(0), x2.shape[0], K,
+               ctypes.c_float(eps), _stream())
+    return out.view(x.shape)
+
+
+def layernorm(x, gamma, beta, eps, add=None, out=None, out2=None):
+    """y = LN(x); if `add` [add_rows, K] is given also returns y2 = y + add[row % add_rows]."""
+    _req_cuda(x, gamma)
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    assert x2.stride(1) == 1
+    out = torch.empty((x2.shape[0], K), dtype=x.dtype, device=x.device) if out is None else out
+    if add is not None:
+        out2 = torch.empty_like(out) if out2 is None else out2
+        add_rows = add.shape[0]
+    else:
+        add_rows = 0
+    _capi.call("ss_layernorm", _dt(x), _p(x2), x2.stride(0), _p(gamma), _p(beta), _p(out), out.stride(0), x2.shape[0],
+               K, ctypes.c_float(eps), _p(add), add_rows, _p(out2), out2.stride(0) if out2 is not None else 0,
+               _stream())
+    shp = x.shape
+    if add is not None:
+        return out.view(shp), out2.view(shp)
+    return out.view(shp)
+
+
+def l2norm_tokens(x):
+    _req_cuda(x)
+    B, T, C = x.shape
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _capi.call("ss_l2norm_tokens_f16", _p(x), _p(y), B, T, C, _stream())
+    return y
+
+
+EPI_NONE, EPI_RESIDUAL, EPI_SWIGLU = 0, 1, 2
+
+
+def skinny_gemm(x, W, epilogue=EPI_NONE, residual=None, out=None):
+    """x [B<=8, K] @ W[N, K]^T with the decode epilogues."""
+    _req_cuda(x, W)
+    B, K = x.shape
+    N = W.shape[0]
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    out = torch.empty((B, n_out), dtype=x.dtype, device=x.device) if out is None else out
+    _capi.call("ss_skinny_gemm_f16", _p(x), x.stride(0), _p(W), _p(out), out.stride(0), B, N, K, epilogue,
+               _p(residual), residual.stride(0) if residual is not None else 0, _stream())
+    return out
+
+
+def rope_kv_append(qkv, q_out, kcache, vcache, tok_seq, tok_pos, tok_slot, page_table, cos_t, sin_t, H, D):
+    ntok = qkv.shape[0]
+    _capi.call("ss_rope_kv_append_f16", _p(qkv), qkv.stride(0), _p(q_out), _p(kcache), _p(vcache), _p(tok_seq),
+               _p(tok_pos), _p(tok_slot), ntok, _p(page_table), page_table.shape[1], _p(cos_t), _p(sin_t), H, D,
+               _stream())
+
+
+def attn_decode_paged(q, kcache, vcache, seq_lens, page_table, out, workspace, H, D, splits, scale):
+    B = q.shape[0]
+    _capi.call("ss_attn_decode_paged_f16", _p(q), _p(kcache), _p(vcache), _p(seq_lens), _p(page_table),
+               page_table.shape[1], _p(out), _p(workspace), B, H, D, splits, ctypes.c_float(scale), _stream())
+
+
+def logits_process_argmax(logits, last_ids, img_ids, next_ids):
+    B, V = logits.shape
+    _capi.call("ss_logits_process_argmax_f16", _p(logits), logits.stride(0), V, _p(last_ids), _p(img_ids),
+               img_ids.numel() if img_ids is not None else 0, _p(next_ids), B, _stream())
+
+
+def gather_rows(table, ids, out):
+    _capi.call("ss_gather_rows_16b", _p(table), _p(ids), _p(out), out.stride(0), ids.numel(), table.shape[1],
+               _stream())
+
+
+def decode_advance(next_ids, cur_ids, tok_pos, tok_slot, seq_lens, out_ids, n_out, done, eos_id):
+    B = next_ids.numel()
+    _capi.call("ss_decode_advance", _p(next_ids), _p(cur_ids), _p(tok_pos), _p(tok_slot), _p(seq_lens), _p(out_ids),
+               out_ids.shape[1], _p(n_out), _p(done), eos_id, B, _stream())
+
+
+ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+GLU_NONE, GLU_GEGLU, GLU_SWIGLU = 0, 1, 2
+
+
+def gemm(a, w, bias=None, bias2=None, rows_per_group=0, residual=None, act=ACT_NONE, glu=GLU_NONE, alpha=1.0,
+         out=None, force_bn=0):
+    """out[M, N or N/2] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores."""
+    _req_cuda(a, w)
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if glu else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=a.dtype, device=a.device)
+    assert out.stride(1) == 1
+    _capi.call("ss_gemm_tn", _dt(a), _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
+               _p(bias), _p(bias2), rows_per_group, _p(residual), residual.stride(0) if residual is not None else 0,
+               act, glu, ctypes.c_float(alpha), force_bn, _stream())
+    return out
+
+
+def conv3x3(x, w, bias=None, bias2=None, residual=None, act=ACT_NONE, out=None, force_bn=0):
+    """x NHWC [N,H,W,Cin], w [Cout, 9*Cin] (tap-major), out NHWC [N,H,W,Cout]."""
+    _req_cuda(x, w)
+    Nimg, H, W_, Cin = x.shape
+    Cout = w.shape[0]
+    assert x.is_contiguous() and w.is_contiguous() and w.shape[1] == 9 * Cin
+    if out is None:
+        out = torch.empty((Nimg, H, W_, Cout), dtype=x.dtype, device=x.device)
+    _capi.call("ss_conv3x3_nhwc", _dt(x), _p(x), _p(w), _p(out), Nimg, H, W_, Cin, Cout, _p(bias), _p(bias2),
+               _p(residual), act, force_bn, _stream())
+    return out

@@ -1,0 +1,228 @@
+"""Op-level parity of the CUDA kernels (through the C-ABI) against plain fp32 torch math."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, ref, rtol=2e-3, atol=None, what=""):
+    got = got.float()
+    ref = ref.float()
+    if atol is None:
+        atol = 2e-3 * ref.abs().max().item() + 1e-6
+    err = (got - ref).abs()
+    bad = err > (atol + rtol * ref.abs())
+    assert not bad.any(), f"{what}: {bad.sum().item()} / {bad.numel()} out of tolerance, max err {err.max().item():.4g} (atol {atol:.3g})"
+
+
+def test_rmsnorm(cuda_dev):
+    from seedstory import ops
+    torch.manual_seed(0)
+    for rows, K in [(1, 4096), (5, 4096), (3, 11008), (66, 4096)]:
+        x = torch.randn(rows, K, device=cuda_dev).half()
+        w = (1 + 0.1 * torch.randn(K, device=cuda_dev)).half()
+        y = ops.rmsnorm(x, w, 1e-5)
+        var = x.float().pow(2).mean(-1, keepdim=True)
+        ref = w * (x * torch.rsqrt(var + 1e-5)).half()
+        _close(y, ref, rtol=1e-3, atol=1e-3, what=f"rmsnorm {rows}x{K}")
+
+
+def test_layernorm(cuda_dev):
+    from seedstory import ops
+    torch.manual_seed(0)
+    for dt in (torch.float16, torch.bfloat16):
+        x = torch.randn(77, 1664, device=cuda_dev).to(dt)
+        g = (1 + 0.1 * torch.randn(1664, device=cuda_dev)).to(dt)
+        b = (0.1 * torch.randn(1664, device=cuda_dev)).to(dt)
+        add = torch.randn(7, 1664, device=cuda_dev).to(dt)
+        y, y2 = ops.layernorm(x, g, b, 1e-6, add=add)
+        ref = torch.nn.functional.layer_norm(x.float(), (1664,), g.float(), b.float(), 1e-6)
+        tol = 2e-3 if dt == torch.float16 else 1.6e-2
+        _close(y, ref, rtol=tol, atol=tol, what="layernorm")
+        ref2 = ref.to(dt).float() + add.float().repeat(11, 1)
+        _close(y2, ref2, rtol=tol, atol=2 * tol, what="layernorm+add")
+
+
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_skinny_gemm(cuda_dev, B):
+    from seedstory import ops
+    torch.manual_seed(B)
+    for N, K in [(4096, 4096), (12288, 4096), (4096, 11008), (32066, 4096)]:
+        x = torch.randn(B, K, device=cuda_dev).half()
+        W = (torch.randn(N, K, device=cuda_dev) * 0.02).half()
+        ref = x.float() @ W.float().t()
+        y = ops.skinny_gemm(x, W)
+        _close(y, ref, what=f"skinny {B}x{N}x{K}")
+        res = torch.randn(B, N, device=cuda_dev).half()
+        y = ops.skinny_gemm(x, W, ops.EPI_RESIDUAL, residual=res)
+        _close(y, ref.half().float() + res.float(), what="skinny+res")
+    # SwiGLU with pairwise interleaved gate/up rows
+    K, I = 4096, 11008
+    x = torch.randn(B, K, device=cuda_dev).half()
+    Wg = (torch.randn(I, K, device=cuda_dev) * 0.02).half()
+    Wu = (torch.randn(I, K, device=cuda_dev) * 0.02).half()
+    Wp = torch.stack([Wg, Wu], dim=1).reshape(2 * I, K).contiguous()
+    y = ops.skinny_gemm(x, Wp, ops.EPI_SWIGLU)
+    g = (x.float() @ Wg.float().t()).half()
+    u = (x.float() @ Wu.float().t()).half()
+    ref = torch.nn.functional.silu(g.float()).half() * u
+    _close(y, ref, what="skinny swiglu")
+
+
+def _rope_tables(D, maxpos, dev):
+    inv = 1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))
+    t = torch.arange(maxpos).float()
+    fr = torch.einsum("i,j->ij", t, inv)
+    emb = torch.cat((fr, fr), -1)
+    return emb.cos().half().to(dev), emb.sin().half().to(dev)
+
+
+def test_rope_append_and_decode_attention(cuda_dev):
+    from seedstory import ops
+    torch.manual_seed(1)
+    H, D, B = 32, 128, 3
+    lens = [131, 1041, 700]
+    max_pages = 32
+    npages = B * max_pages
+    kc = torch.zeros(npages, H, 64, D, device=cuda_dev, dtype=torch.float16)
+    vc = torch.zeros_like(kc)
+    # scrambled page table: sequence b uses pages in a permuted order
+    perm = torch.randperm(npages, device=cuda_dev).int().view(B, max_pages).contiguous()
+    cos_t, sin_t = _rope_tables(D, 4096, cuda_dev)
+    ks, vs = [], []
+    for b, n in enumerate(lens):
+        qkv = torch.randn(n, 3 * H * D, device=cuda_dev).half()
+        pos = torch.arange(n, device=cuda_dev, dtype=torch.int32) + 5 * b  # position != slot on purpose
+        slot = torch.arange(n, device=cuda_dev, dtype=torch.int32)
+        seq = torch.full((n,), b, device=cuda_dev, dtype=torch.int32)
+        qo = torch.empty(n, H * D, device=cuda_dev, dtype=torch.float16)
+        ops.rope_kv_append(qkv, qo, kc, vc, seq, pos, slot, perm, cos_t, sin_t, H, D)
+        q, k, v = qkv.view(n, 3, H, D).unbind(1)
+        cos = cos_t[pos.long()][:, None, :]
+        sin = sin_t[pos.long()][:, None, :]
+
+        def rot(x):
+            return torch.cat((-x[..., D // 2:], x[..., :D // 2]), -1)
+        q_ref = (q * cos) + (rot(q) * sin)
+        k_ref = (k * cos) + (rot(k) * sin)
+        assert torch.equal(qo.view(n, H, D), q_ref), "rope(q) must be bit-exact"
+        # read back the cache through the page table
+        pages = perm[b, : (n + 63) // 64].long()
+        k_back = kc[pages].permute(0, 2, 1, 3).reshape(-1, H, D)[:n]
+        v_back = vc[pages].permute(0, 2, 1, 3).reshape(-1, H, D)[:n]
+        assert torch.equal(k_back, k_ref) and torch.equal(v_back, v)
+        ks.append(k_ref)
+        vs.append(v)
+    # decode attention: one query per sequence attends to everything cached
+    q = torch.randn(B, H * D, device=cuda_dev).half()
+    seq_lens = torch.tensor(lens, device=cuda_dev, dtype=torch.int32)
+    for splits in (2, 8):
+        out = torch.empty(B, H * D, device=cuda_dev, dtype=torch.float16)
+        ws = torch.empty(B * H * splits * (D + 2), device=cuda_dev, dtype=torch.float32)
+        ops.attn_decode_paged(q, kc, vc, seq_lens, perm, out, ws, H, D, splits, 1.0 / math.sqrt(D))
+        for b, n in enumerate(lens):
+            qq = q[b].view(H, 1, D).float()
+            kk = ks[b].permute(1, 0, 2).float()
+            vv = vs[b].permute(1, 0, 2).float()
+            p = torch.softmax(qq @ kk.transpose(1, 2) / math.sqrt(D), -1)
+            ref = (p @ vv).reshape(H * D)
+            _close(out[b], ref, rtol=2e-3, atol=2e-3, what=f"decode attn b={b} splits={splits}")
+
+
+def test_logits_processor_argmax(cuda_dev):
+    from seedstory import ops
+    torch.manual_seed(2)
+    V = 32066
+    img_ids = torch.tensor([32000] + list(range(32002, 32066)) + [32001], device=cuda_dev, dtype=torch.int32)
+    B = 4
+    logits = torch.randn(B, V, device=cuda_dev).half()
+    logits[0, 32010] = 50.0          # would win, but gets zeroed (not in an image run)
+    logits[0, :32000] -= 10.0        # everything else negative -> zeroed ids win at 0.0, lowest index first
+    last = torch.tensor([17, 32000, 32002 + 63, 32001], device=cuda_dev, dtype=torch.int32)
+    ref_logits = logits.clone()
+    nxt = torch.empty(B, device=cuda_dev, dtype=torch.int32)
+    ops.logits_process_argmax(logits, last, img_ids, nxt)
+    ids = img_ids.tolist()
+    exp = []
+    for b in range(B):
+        row = ref_logits[b].clone()
+        cur = last[b].item()
+        if cur in ids[:-1]:
+            row[ids[ids.index(cur) + 1]] = row.max() + 10.0
+        else:
+            row[torch.tensor(ids[1:], device=cuda_dev).long()] = 0.0
+        exp.append(int(torch.argmax(row.float()).item()))
+        assert torch.equal(row, logits[b]), "in-place edit of the logits row must match the reference processor"
+    assert nxt.tolist() == exp, (nxt.tolist(), exp)
+    assert exp[0] == 32001 and exp[1] == 32002 and exp[2] == 32001
+    # processor disabled
+    ops.logits_process_argmax(ref_logits, last, None, nxt)
+    assert nxt.tolist() == torch.argmax(ref_logits.float(), -1).tolist()
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_gemm_tn_shapes(cuda_dev, dt):
+    from seedstory import ops
+    torch.manual_seed(3)
+    tol = 2e-3 if dt == torch.float16 else 1.6e-2
+    shapes = [(128, 128, 64), (128, 256, 512), (200, 320, 328), (1041, 4096, 4096), (1024, 4992, 1664),
+              (64, 4096, 4096), (4096, 640, 640), (333, 72, 200)]
+    for (M, N, K) in shapes:
+        a = torch.randn(M, K, device=cuda_dev).to(dt)
+        w = (torch.randn(N, K, device=cuda_dev) / math.sqrt(K)).to(dt)
+        ref = a.float() @ w.float().t()
+        for bn in (0, 64, 128, 256):
+            c = ops.gemm(a, w, force_bn=bn)
+            _close(c, ref, rtol=tol, atol=tol * ref.abs().max().item(), what=f"gemm {M}x{N}x{K} bn={bn} {dt}")
+
+
+def test_gemm_tn_epilogues(cuda_dev):
+    from seedstory import ops
+    torch.manual_seed(4)
+    M, N, K = 300, 640, 320
+    a = torch.randn(M, K, device=cuda_dev).half()
+    w = (torch.randn(N, K, device=cuda_dev) / math.sqrt(K)).half()
+    bias = torch.randn(N, device=cuda_dev).half()
+    res = torch.randn(M, N, device=cuda_dev).half()
+    b2 = torch.randn(3, N, device=cuda_dev).half()
+    lin = (a.float() @ w.float().t() + bias.float()).half()
+    c = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, residual=res)
+    ref = torch.nn.functional.gelu(lin.float()).half().float() + res.float()
+    _close(c, ref, what="bias+gelu+res")
+    c = ops.gemm(a, w, bias=bias, bias2=b2, rows_per_group=100, act=ops.ACT_SILU)
+    ref = torch.nn.functional.silu((lin.float() + b2.float().repeat_interleave(100, 0)).half().float())
+    _close(c, ref, what="bias+bias2+silu")
+    c = ops.gemm(a, w, alpha=0.125)
+    _close(c, 0.125 * (a.float() @ w.float().t()), what="alpha")
+    # GLU epilogues over interleaved column pairs
+    wp = w.view(2, N // 2, K).permute(1, 0, 2).reshape(N, K).contiguous()          # rows (first_j, second_j)
+    bp = bias.view(2, N // 2).t().reshape(N).contiguous()
+    first, second = lin[:, : N // 2], lin[:, N // 2:]
+    c = ops.gemm(a, wp, bias=bp, glu=ops.GLU_GEGLU)
+    _close(c, first.float() * torch.nn.functional.gelu(second.float()).half().float(), what="geglu")
+    c = ops.gemm(a, wp, bias=bp, glu=ops.GLU_SWIGLU)
+    _close(c, torch.nn.functional.silu(first.float()).half().float() * second.float(), what="swiglu")
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_conv3x3(cuda_dev, dt):
+    from seedstory import ops
+    torch.manual_seed(5)
+    tol = 3e-3 if dt == torch.float16 else 2e-2
+    for (Nimg, H, W, Cin, Cout) in [(2, 32, 32, 64, 64), (1, 64, 64, 320, 640), (2, 128, 128, 128, 320),
+                                    (1, 256, 256, 64, 128)]:
+        x = torch.randn(Nimg, Cin, H, W, device=cuda_dev).to(dt)
+        w = (torch.randn(Cout, Cin, 3, 3, device=cuda_dev) / math.sqrt(9 * Cin)).to(dt)
+        bias = torch.randn(Cout, device=cuda_dev).to(dt)
+        temb = torch.randn(Nimg, Cout, device=cuda_dev).to(dt)
+        res = torch.randn(Nimg, H, W, Cout, device=cuda_dev).to(dt)
+        ref = torch.nn.functional.conv2d(x.float(), w.float(), bias.float(), padding=1)
+        x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+        w_p = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+        y = ops.conv3x3(x_nhwc, w_p, bias=bias)
+        _close(y.permute(0, 3, 1, 2), ref, rtol=tol, atol=tol * ref.abs().max().item(), what=f"conv {H}x{W} {Cin}->{Cout}")
+        y = ops.conv3x3(x_nhwc, w_p, bias=bias, bias2=temb, residual=res)
+        ref2 = (ref.to(dt).float() + temb.float()[:, :, None, None]).to(dt).float() + res.permute(0, 3, 1, 2).float()
+        _close(y.permute(0, 3, 1, 2), ref2, rtol=tol, atol=tol * ref2.abs().max().item(), what="conv+temb+res")
