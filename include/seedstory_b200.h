@@ -96,4 +96,51 @@ SS_EXPORT int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, 
                               int Cout, const void* bias, const void* bias2, const void* residual, int act,
                               int force_bn, void* stream);
 
+/* ---- fused attention ---------------------------------------------------------------------------- */
+/* softmax(scale * Q K^T [+ bottom-right causal mask]) V, fp16, head_dim 64/128, explicit (batch, token, head)
+ * strides in elements.  Replaces xops.memory_efficient_attention (modeling_llama_xformer.py:282-295, causal=1,
+ * K/V through page_table), the ViT bmm/softmax/bmm (src/models/qwen_visual.py:208-217), nn.MultiheadAttention
+ * inside Resampler (:146-149), PerceiverAttention / AttentionPool2d (src/models_ipa/resampler.py:68-73, 95-113)
+ * and the diffusers Attention processors of the SDXL UNet.  kv_lens (device, optional) overrides Lk per batch
+ * entry; with page_table != NULL k/v are page pools [page][H][64][D]. */
+SS_EXPORT int ss_fmha_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int Lq, int Lk, int D,
+                          long long q_sb, long long q_sl, long long q_sh, long long k_sb, long long k_sl,
+                          long long k_sh, long long v_sb, long long v_sl, long long v_sh, long long o_sb,
+                          long long o_sl, long long o_sh, const int* kv_lens, const int* page_table, int max_pages,
+                          float scale, int causal, void* stream);
+
+/* ---- bandwidth-bound glue ------------------------------------------------------------------------ */
+/* conv1 patchify of the ViT (src/models/qwen_visual.py:347,382): NCHW image -> [B*G*G, Kpad] rows */
+SS_EXPORT int ss_im2col_patch_f16(const void* img, void* out, int B, int C, int S, int P, int Kpad, void* stream);
+/* y[r] = x[r] + add[r % period] — positional embedding adds (qwen_visual.py:387) */
+SS_EXPORT int ss_add_bcast(int dtype, const void* x, const void* add, void* y, long long rows, int C, int period,
+                           void* stream);
+/* dst[dst_rows[i]] = src[i] — input_embeds[ids_cmp_mask] = image_embeds_lm[...] (src/models_clm/models.py:135) */
+SS_EXPORT int ss_scatter_rows_16b(const void* src, const int* dst_rows, void* dst, int ld_dst, int n, int width,
+                                  void* stream);
+/* nn.GroupNorm(32, C) (+ optional fused SiLU) on NHWC — diffusers ResnetBlock2D / Transformer2DModel / VAE norms
+ * (SURVEY.md Appendix C).  stats_ws: 2*N*groups floats. */
+SS_EXPORT int ss_groupnorm_nhwc(int dtype, const void* x, void* y, const void* gamma, const void* beta,
+                                float* stats_ws, int N, int HW, int C, int groups, float eps, int silu, void* stream);
+/* Upsample2D's F.interpolate(scale_factor=2, mode="nearest") on NHWC */
+SS_EXPORT int ss_upsample2x_nhwc_16b(const void* x, void* y, int N, int H, int W, int C, void* stream);
+/* torch.cat([hidden, skip], dim=1) of the UNet up blocks, on NHWC rows */
+SS_EXPORT int ss_concat_channels_16b(const void* a, const void* b, void* out, long long rows, int Ca, int Cb,
+                                     void* stream);
+/* im2col for Downsample2D's stride-2 3x3 conv (pad 1); feeds ss_gemm_tn */
+SS_EXPORT int ss_im2col3x3_s2_nhwc_16b(const void* x, void* cols, int N, int H, int W, int C, void* stream);
+/* classifier-free guidance + EulerDiscreteScheduler.step (eps-prediction) + scale_model_input of the next step —
+ * the per-step glue of StableDiffusionXLPipeline.__call__ reached from src/models_ipa/adapter_modules.py:455-466 */
+SS_EXPORT int ss_cfg_euler_step_f16(const void* eps, int eps_ld, void* latents, void* next_in, int in_ld, int HW,
+                                    int C, float guidance, float sigma, float sigma_next, void* stream);
+SS_EXPORT int ss_cast_scale(int dtype_in, const void* x, int dtype_out, void* y, long long n, float scale,
+                            void* stream);
+/* in-place softmax(scale * row) — VAE mid-block single-head attention over 16384 tokens */
+SS_EXPORT int ss_softmax_rows(int dtype, void* x, int ld, int rows, int n, float scale, void* stream);
+SS_EXPORT int ss_transpose_16b(const void* x, void* y, int R, int C, void* stream);
+/* x.mean(dim=tokens) — AttentionPool2d (src/models_ipa/resampler.py:92) */
+SS_EXPORT int ss_mean_tokens_f16(const void* x, void* y, int B, int T, int C, void* stream);
+/* VaeImageProcessor.postprocess: (x/2+0.5).clamp(0,1)*255 round -> uint8 HWC */
+SS_EXPORT int ss_image_to_uint8(int dtype, const void* x, int ldx, void* out, long long pixels, int C, void* stream);
+
 #endif /* SEEDSTORY_B200_H */

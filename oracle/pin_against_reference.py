@@ -1,0 +1,198 @@
+"""ORACLE PINNING — runs only in the build container (needs /root/reference; never on the GPU box).
+
+Imports the reference's own modules, runs them on seeded random weights at small dims (CPU fp32) next to
+the oracle restatements, asserts agreement, and freezes input/output vectors under tests/golden/ so that
+the CPU test suite and the GPU parity tests have reference-generated fixtures.
+
+    python oracle/pin_against_reference.py            # writes tests/golden/*.pt
+
+Reference pieces exercised (file:line):
+  src/models_clm/modeling_llama_xformer.py:703-794 (LlamaForCausalLM.forward, xformers -> SDPA stand-in)
+  src/models_clm/generation.py:9-31              (AutoImageTokenGenerationProcessor)
+  src/models/qwen_visual.py:376-399, 138-150       (ViT + attn-pool, agent Resampler)
+  src/models_ipa/resampler.py:228-284             (ResamplerXLV2)
+"""
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("SEEDSTORY_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import llama_oracle as LO  # noqa: E402
+from oracle import vision_oracle as VO  # noqa: E402
+
+
+def _install_xformers_stub():
+    """xformers is not installed: stand in for the two symbols the reference touches
+    (modeling_llama_xformer.py:282-295) with SDPA + an explicit bottom-right causal mask."""
+    xf = types.ModuleType("xformers")
+    xops = types.ModuleType("xformers.ops")
+    fmha = types.ModuleType("xformers.ops.fmha")
+    ab = types.ModuleType("xformers.ops.fmha.attn_bias")
+
+    class LowerTriangularFromBottomRightMask:
+        pass
+
+    class LowerTriangularMask:
+        pass
+
+    def memory_efficient_attention(q, k, v, attn_bias=None):
+        # q,k,v: [B, T, H, D]
+        tq, tk = q.shape[1], k.shape[1]
+        qi = torch.arange(tq).unsqueeze(1)
+        kj = torch.arange(tk).unsqueeze(0)
+        if isinstance(attn_bias, LowerTriangularFromBottomRightMask):
+            mask = kj <= qi + (tk - tq)
+        else:
+            mask = kj <= qi
+        o = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                             attn_mask=mask)
+        return o.transpose(1, 2)
+    ab.LowerTriangularFromBottomRightMask = LowerTriangularFromBottomRightMask
+    fmha.attn_bias = ab
+    xops.fmha = fmha
+    xops.LowerTriangularMask = LowerTriangularMask
+    xops.memory_efficient_attention = memory_efficient_attention
+    xf.ops = xops
+    for n, m in {"xformers": xf, "xformers.ops": xops, "xformers.ops.fmha": fmha,
+                 "xformers.ops.fmha.attn_bias": ab}.items():
+        sys.modules[n] = m
+
+
+def _maxdiff(a, b):
+    return (a.float() - b.float()).abs().max().item()
+
+
+def pin_llama():
+    _install_xformers_stub()
+    sys.path.insert(0, REF)
+    from src.models_clm import modeling_llama_xformer as M  # the reference file itself
+    from transformers import LlamaConfig
+    hidden, inter, heads, layers, vocab = 128, 352, 4, 3, 320
+    cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads,
+                      num_hidden_layers=layers, vocab_size=vocab, rms_norm_eps=1e-5, max_position_embeddings=512,
+                      pad_token_id=0)
+    cfg._attn_implementation = "eager"
+    ref = M.LlamaForCausalLM(cfg).eval()
+    p = LO.LlamaParams.random(hidden, inter, heads, layers, vocab, lora_r=0, seed=7, std=0.05)
+    sd = {"model.embed_tokens.weight": p.embed, "model.norm.weight": p.norm, "lm_head.weight": p.lm_head}
+    for i, L in enumerate(p.layers):
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[f"model.layers.{i}.self_attn.{n}.weight"] = L[n]
+        for n in ("gate_proj", "up_proj", "down_proj"):
+            sd[f"model.layers.{i}.mlp.{n}.weight"] = L[n]
+        sd[f"model.layers.{i}.input_layernorm.weight"] = L["input_layernorm"]
+        sd[f"model.layers.{i}.post_attention_layernorm.weight"] = L["post_attention_layernorm"]
+    missing, unexpected = ref.load_state_dict(sd, strict=False)
+    assert not [m for m in missing if "rotary" not in m and "inv_freq" not in m], missing
+    ref.use_kv_cache_head = False
+    g = torch.Generator().manual_seed(11)
+    T0, T1 = 37, 5
+    emb0 = torch.randn(1, T0, hidden, generator=g) * 0.5
+    pos0 = torch.arange(T0).unsqueeze(0)
+    with torch.no_grad():
+        out0 = ref(input_ids=torch.zeros(1, T0, dtype=torch.long), inputs_embeds=emb0, position_ids=pos0,
+                   use_cache=True, output_hidden_states=True, return_dict=True)
+        lo0, hn0, kv0 = LO.model_forward(p, emb0, pos0, None, max_pos=512)
+    d = _maxdiff(out0.logits, lo0)
+    assert d < 2e-4, d
+    assert _maxdiff(out0.hidden_states[-1], hn0) < 2e-4
+    # second call: 5-token chunk on top of the cache, window-relative positions (bottom-right mask exercised)
+    emb1 = torch.randn(1, T1, hidden, generator=g) * 0.5
+    pos1 = (torch.arange(T1) + T0).unsqueeze(0)
+    with torch.no_grad():
+        out1 = ref(input_ids=torch.zeros(1, T1, dtype=torch.long), inputs_embeds=emb1, position_ids=pos1,
+                   past_key_values=out0.past_key_values, use_cache=True, output_hidden_states=True, return_dict=True)
+        lo1, hn1, kv1 = LO.model_forward(p, emb1, pos1, kv0, max_pos=512)
+    assert _maxdiff(out1.logits, lo1) < 2e-4
+    assert _maxdiff(out1.past_key_values[1][0], kv1[1][0]) < 1e-5  # post-RoPE keys
+    print("llama forward pinned: max logits diff", d)
+    torch.save({"cfg": dict(hidden=hidden, inter=inter, heads=heads, layers=layers, vocab=vocab, eps=1e-5, seed=7,
+                            std=0.05),
+                "emb0": emb0, "emb1": emb1, "logits0": out0.logits, "logits1": out1.logits,
+                "hidden0": out0.hidden_states[-1], "k_layer1": out1.past_key_values[1][0]},
+               os.path.join(GOLD, "llama_forward.pt"))
+
+    # logits processor: the reference class with a fake tokenizer
+    from src.models_clm.generation import AutoImageTokenGenerationProcessor
+
+    class Tok:
+        def encode(self, s, add_special_tokens=False):
+            return [300] + list(range(302, 302 + 8)) + [301]
+    proc = AutoImageTokenGenerationProcessor(Tok(), num_img_gen_tokens=8)
+    img_ids = proc.img_ids_list
+    cases = []
+    for last in (5, 300, 303, 309, 301):
+        sc = torch.randn(1, vocab, generator=g)
+        exp = proc(torch.tensor([[1, 2, last]]), sc.clone())
+        got = LO.image_token_processor(last, sc[0].clone(), img_ids)
+        assert torch.equal(exp[0], got)
+        cases.append({"last": last, "scores": sc[0], "out": exp[0]})
+    torch.save({"img_ids": img_ids, "cases": cases}, os.path.join(GOLD, "logits_processor.pt"))
+    print("logits processor pinned")
+
+
+def pin_vision():
+    sys.path.insert(0, REF)
+    from src.models import qwen_visual as QV
+    from src.models_ipa import resampler as RS
+    torch.manual_seed(3)
+    # small ViT: width 64, 4 heads (head_dim 16), 2 layers, 56x56 image, patch 14 -> 16 tokens; pos table is 256 (16x16)
+    vit = QV.VisionTransformerWithAttnPool(image_size=56, patch_size=14, width=64, layers=2, heads=4,
+                                           mlp_ratio=4.0, n_queries=16, output_dim=256).eval()
+    with torch.no_grad():
+        for prm in vit.parameters():
+            if prm.requires_grad:
+                prm.add_(torch.randn_like(prm) * 0.05)
+    img = torch.randn(2, 3, 56, 56)
+    with torch.no_grad():
+        ref = vit(img)
+        got = VO.vit_forward(vit.state_dict(), img, heads=4, layers=2, patch=14)
+    d = _maxdiff(ref, got)
+    assert d < 1e-4, d
+    print("vit pinned: max diff", d)
+    torch.save({"sd": vit.state_dict(), "img": img, "out": ref,
+                "cfg": dict(image_size=56, patch_size=14, width=64, layers=2, heads=4, mlp_ratio=4.0, n_queries=16,
+                            output_dim=256)}, os.path.join(GOLD, "vit_small.pt"))
+
+    # agent resamplers (grid 8 over 256 keys -> bicubic up; grid 16 over 64 keys -> bicubic down)
+    for name, grid, L in (("resampler_in", 8, 256), ("resampler_out", 16, 64)):
+        rs = QV.Resampler(grid_size=grid, embed_dim=256, num_heads=2, kv_dim=256).eval()
+        with torch.no_grad():
+            for prm in rs.parameters():
+                if prm.requires_grad:
+                    prm.add_(torch.randn_like(prm) * 0.05)
+        x = torch.randn(2, L, 256)
+        with torch.no_grad():
+            ref = rs(x)
+            got = VO.resampler(rs.state_dict(), x, heads=2)
+        d = _maxdiff(ref, got)
+        assert d < 1e-4, d
+        print(name, "pinned: max diff", d)
+        torch.save({"sd": rs.state_dict(), "x": x, "out": ref, "grid": grid, "heads": 2},
+                   os.path.join(GOLD, f"{name}.pt"))
+
+    xl = RS.ResamplerXLV2(dim=128, depth=2, dim_head=32, heads=4, num_queries=16, embedding_dim=256, output1_dim=96,
+                          output2_dim=160, ff_mult=4).eval()
+    x = torch.randn(2, 64, 256)
+    with torch.no_grad():
+        r1, r2 = xl(x)
+        g1, g2 = VO.resampler_xl_v2(xl.state_dict(), x, depth=2, heads=4)
+    d = max(_maxdiff(r1, g1), _maxdiff(r2, g2))
+    assert d < 1e-4, d
+    print("ResamplerXLV2 pinned: max diff", d)
+    torch.save({"sd": xl.state_dict(), "x": x, "out1": r1, "out2": r2,
+                "cfg": dict(dim=128, depth=2, dim_head=32, heads=4, num_queries=16, embedding_dim=256,
+                            output1_dim=96, output2_dim=160, ff_mult=4)}, os.path.join(GOLD, "resampler_xlv2.pt"))
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    pin_llama()
+    pin_vision()
+    print("golden vectors written to", GOLD)

@@ -1,0 +1,419 @@
+// Bandwidth-bound glue kernels of the visual / de-tokenizer path: patchify, broadcast adds, row scatter,
+// GroupNorm(+SiLU) on NHWC, nearest 2x upsample, channel concat, stride-2 im2col, CFG + Euler update,
+// softmax rows, transposes, dtype casts, image post-processing.  All are vectorised 16-byte accesses
+// over NHWC / token-major tensors (C innermost), grid-stride over 148*k CTAs.
+#include "common.cuh"
+
+namespace {
+constexpr int EW_THREADS = 256;
+inline int ew_grid(long long work_items) {
+  long long g = (work_items + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+}  // namespace
+
+// ---- ViT patchify: NCHW image -> [B*G*G, Kpad] rows, k = c*P*P + ky*P + kx (conv1 weight flatten order,
+// src/models/qwen_visual.py:347,382) --------------------------------------------------------------
+__global__ void im2col_patch_kernel(const __half* __restrict__ img, __half* __restrict__ out, int B, int C, int S,
+                                    int P, int Kpad) {
+  const int G = S / P;
+  const long long total = (long long)B * G * G * Kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    const long long row = i / Kpad;
+    __half v = __float2half_rn(0.f);
+    if (k < C * P * P) {
+      const int c = k / (P * P), ky = (k / P) % P, kx = k % P;
+      const int gx = (int)(row % G), gy = (int)((row / G) % G), b = (int)(row / ((long long)G * G));
+      v = img[(((long long)b * C + c) * S + gy * P + ky) * S + gx * P + kx];
+    }
+    out[i] = v;
+  }
+}
+SS_API int ss_im2col_patch_f16(const void* img, void* out, int B, int C, int S, int P, int Kpad, void* stream) {
+  SS_REQUIRE(S % P == 0 && Kpad >= C * P * P, "bad patch geometry");
+  const long long total = (long long)B * (S / P) * (S / P) * Kpad;
+  im2col_patch_kernel<<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const __half*)img, (__half*)out, B, C, S,
+                                                                             P, Kpad);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- y[r, :] = x[r, :] + add[r % period, :]  (positional-embedding adds, fp16/bf16 add semantics) ----
+template <typename T>
+__global__ void add_bcast_kernel(const T* __restrict__ x, const T* __restrict__ add, T* __restrict__ y, long long rows,
+                                 int C, int period) {
+  const int vecs = C >> 3;
+  const long long total = rows * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vecs;
+    const int v = (int)(i % vecs);
+    float a[8], b[8];
+    unpack8<T>(ld_cached16(x + r * C + v * 8), a);
+    unpack8<T>(ld_cached16(add + (r % period) * C + v * 8), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    st16(y + r * C + v * 8, pack8<T>(a));
+  }
+}
+SS_API int ss_add_bcast(int dtype, const void* x, const void* add, void* y, long long rows, int C, int period,
+                        void* stream) {
+  SS_REQUIRE(C % 8 == 0 && period > 0, "C % 8, period > 0");
+  if (rows == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = ew_grid(rows * (C / 8));
+  if (dtype == SS_F16)
+    add_bcast_kernel<__half><<<g, EW_THREADS, 0, s>>>((const __half*)x, (const __half*)add, (__half*)y, rows, C, period);
+  else
+    add_bcast_kernel<__nv_bfloat16><<<g, EW_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)add,
+                                                             (__nv_bfloat16*)y, rows, C, period);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- dst[dst_rows[i], :] = src[i, :]  (input_embeds[ids_cmp_mask] = image_embeds_lm[...], models.py:135) ----
+__global__ void scatter_rows_kernel(const uint16_t* __restrict__ src, const int* __restrict__ dst_rows,
+                                    uint16_t* __restrict__ dst, int ld_dst, int width) {
+  const int i = blockIdx.x;
+  const vec8* s = reinterpret_cast<const vec8*>(src + (size_t)i * width);
+  vec8* d = reinterpret_cast<vec8*>(dst + (size_t)dst_rows[i] * ld_dst);
+  for (int v = threadIdx.x; v < (width >> 3); v += blockDim.x) d[v] = s[v];
+}
+SS_API int ss_scatter_rows_16b(const void* src, const int* dst_rows, void* dst, int ld_dst, int n, int width,
+                               void* stream) {
+  SS_REQUIRE(width % 8 == 0 && ld_dst % 8 == 0, "width % 8");
+  if (n == 0) return 0;
+  scatter_rows_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, dst_rows, (uint16_t*)dst, ld_dst, width);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- GroupNorm on NHWC (diffusers ResnetBlock2D norm1/norm2, Transformer2D norm, VAE norms) --------
+// pass 1: per-(image, group) sum / sum-of-squares in fp32; pass 2: normalise, affine, optional SiLU.
+template <typename T>
+__global__ void groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int HW, int C, int groups,
+                                       int pix_per_cta) {
+  extern __shared__ float gsm[];  // [2*C]
+  float* csum = gsm;
+  float* csq = gsm + C;
+  const int n = blockIdx.y;
+  const int vecs = C >> 3;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) gsm[i] = 0.f;
+  __syncthreads();
+  const int nl = blockDim.x / vecs;  // pixel lanes
+  const int v = threadIdx.x % vecs, lane = threadIdx.x / vecs;
+  if (lane < nl) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    const T* base = x + ((size_t)n * HW) * C + v * 8;
+    for (int p = p0 + lane; p < p1; p += nl) {
+      float f[8];
+      unpack8<T>(ld_cached16(base + (size_t)p * C), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] += f[j] * f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&csum[v * 8 + j], s[j]);
+      atomicAdd(&csq[v * 8 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  const int cg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      s += csum[c];
+      q += csq[c];
+    }
+    atomicAdd(&stats[((size_t)n * groups + g) * 2], s);
+    atomicAdd(&stats[((size_t)n * groups + g) * 2 + 1], q);
+  }
+}
+
+template <typename T>
+__global__ void groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
+                                       const T* __restrict__ gamma, const T* __restrict__ beta, int HW, int C,
+                                       int groups, float eps, int silu, long long total_vecs) {
+  const int vecs = C >> 3, cg = C / groups;
+  const float inv_cnt = 1.f / ((float)HW * (float)cg);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vecs;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    const long long pix = i / vecs;
+    const int n = (int)(pix / HW);
+    float f[8], gm[8], bt[8];
+    unpack8<T>(ld_cached16(x + pix * C + v * 8), f);
+    unpack8<T>(ld_cached16(gamma + v * 8), gm);
+    unpack8<T>(ld_cached16(beta + v * 8), bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (v * 8 + j) / cg;
+      const float s = stats[((size_t)n * groups + g) * 2], q = stats[((size_t)n * groups + g) * 2 + 1];
+      const float mean = s * inv_cnt;
+      const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+      float o = (f[j] - mean) * rsqrtf(var + eps) * gm[j] + bt[j];
+      if (silu) {
+        o = ss_num<T>::to_f(ss_num<T>::from_f(o));  // GroupNorm output is rounded before the activation module
+        o = o / (1.f + __expf(-o));
+      }
+      f[j] = o;
+    }
+    st16(y + pix * C + v * 8, pack8<T>(f));
+  }
+}
+
+SS_API int ss_groupnorm_nhwc(int dtype, const void* x, void* y, const void* gamma, const void* beta, float* stats_ws,
+                             int N, int HW, int C, int groups, float eps, int silu, void* stream) {
+  SS_REQUIRE(C % 8 == 0 && C % groups == 0 && C <= 4096, "C % 8, C % groups, C <= 4096");
+  SS_REQUIRE(dtype == SS_F16 || dtype == SS_BF16, "dtype");
+  if (N == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  SS_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * N * groups, s));
+  const int vecs = C / 8;
+  int block = vecs <= 256 ? vecs * (256 / vecs) : vecs;
+  SS_REQUIRE(block <= 1024, "C too large for the GroupNorm stats kernel");
+  int chunks = (148 * 4 + N - 1) / N;
+  int pix_per_cta = (HW + chunks - 1) / chunks;
+  if (pix_per_cta < 32) pix_per_cta = 32;
+  chunks = (HW + pix_per_cta - 1) / pix_per_cta;
+  const long long total_vecs = (long long)N * HW * vecs;
+  if (dtype == SS_F16) {
+    groupnorm_stats_kernel<__half><<<dim3(chunks, N), block, 2 * C * sizeof(float), s>>>((const __half*)x, stats_ws, HW,
+                                                                                        C, groups, pix_per_cta);
+    SS_LAUNCH_CHECK();
+    groupnorm_apply_kernel<__half><<<ew_grid(total_vecs), EW_THREADS, 0, s>>>(
+        (const __half*)x, (__half*)y, stats_ws, (const __half*)gamma, (const __half*)beta, HW, C, groups, eps, silu,
+        total_vecs);
+  } else {
+    groupnorm_stats_kernel<__nv_bfloat16><<<dim3(chunks, N), block, 2 * C * sizeof(float), s>>>(
+        (const __nv_bfloat16*)x, stats_ws, HW, C, groups, pix_per_cta);
+    SS_LAUNCH_CHECK();
+    groupnorm_apply_kernel<__nv_bfloat16><<<ew_grid(total_vecs), EW_THREADS, 0, s>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, stats_ws, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+        HW, C, groups, eps, silu, total_vecs);
+  }
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- nearest 2x upsample, NHWC (Upsample2D before its conv) ------------------------------------
+__global__ void upsample2x_kernel(const vec8* __restrict__ x, vec8* __restrict__ y, int N, int H, int W, int vecs) {
+  const long long total = (long long)N * 2 * H * 2 * W * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    long long p = i / vecs;
+    const int ox = (int)(p % (2 * W));
+    p /= 2 * W;
+    const int oy = (int)(p % (2 * H));
+    const int n = (int)(p / (2 * H));
+    y[i] = x[(((long long)n * H + (oy >> 1)) * W + (ox >> 1)) * vecs + v];
+  }
+}
+SS_API int ss_upsample2x_nhwc_16b(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  SS_REQUIRE(C % 8 == 0, "C % 8");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const vec8*)x, (vec8*)y, N, H, W, C / 8);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- channel concat on NHWC rows: out[r] = [a[r] | b[r]] (UNet skip connections) ----------------
+__global__ void concat_rows_kernel(const vec8* __restrict__ a, const vec8* __restrict__ b, vec8* __restrict__ out,
+                                   long long rows, int va, int vb) {
+  const int vo = va + vb;
+  const long long total = rows * vo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vo);
+    const long long r = i / vo;
+    out[i] = v < va ? a[r * va + v] : b[r * vb + (v - va)];
+  }
+}
+SS_API int ss_concat_channels_16b(const void* a, const void* b, void* out, long long rows, int Ca, int Cb,
+                                  void* stream) {
+  SS_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "C % 8");
+  const long long total = rows * ((Ca + Cb) / 8);
+  concat_rows_kernel<<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const vec8*)a, (const vec8*)b, (vec8*)out,
+                                                                             rows, Ca / 8, Cb / 8);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- im2col for the two stride-2 3x3 Downsample2D convs (pad 1): cols[(n,oy,ox), (ky*3+kx)*C + c] ----
+__global__ void im2col_s2_kernel(const vec8* __restrict__ x, vec8* __restrict__ cols, int N, int H, int W, int vecs) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * 9 * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    long long p = i / vecs;
+    const int tap = (int)(p % 9);
+    p /= 9;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    const int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
+    vec8 val{0u, 0u, 0u, 0u};
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = x[(((long long)n * H + iy) * W + ix) * vecs + v];
+    cols[i] = val;
+  }
+}
+SS_API int ss_im2col3x3_s2_nhwc_16b(const void* x, void* cols, int N, int H, int W, int C, void* stream) {
+  SS_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "C % 8, even H/W");
+  const long long total = (long long)N * (H / 2) * (W / 2) * 9 * (C / 8);
+  im2col_s2_kernel<<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const vec8*)x, (vec8*)cols, N, H, W, C / 8);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- classifier-free guidance + Euler step (diffusers EulerDiscreteScheduler.step, eps-prediction) ----
+// eps [2, HW, Cpad] NHWC (row 0 = uncond, row 1 = cond; first C channels valid), latents fp16 [HW, C]
+// (NHWC of the [1,4,128,128] latent).  x <- x + (eu + g (ec - eu)) * (sigma_next - sigma) in fp32, rounded to
+// fp16; also emits the next model input x / sqrt(sigma_next^2 + 1), duplicated for both CFG rows, channel-padded.
+__global__ void cfg_euler_kernel(const __half* __restrict__ eps, int eps_ld, __half* __restrict__ lat,
+                                 __half* __restrict__ next_in, int in_ld, int HW, int C, float guidance, float sigma,
+                                 float sigma_next) {
+  const int total = HW * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int p = i / C, c = i % C;
+    // pipeline: noise_pred = uncond + g*(text - uncond) in fp16 tensors (each op rounded)
+    const __half eu = eps[(size_t)p * eps_ld + c], ec = eps[((size_t)HW + p) * eps_ld + c];
+    const __half diff = __float2half_rn(__half2float(ec) - __half2float(eu));
+    const __half gd = __float2half_rn(guidance * __half2float(diff));
+    const __half e = __float2half_rn(__half2float(eu) + __half2float(gd));
+    // scheduler.step: upcast sample to fp32, pred_original = x - sigma*eps, derivative = (x - pred)/sigma, x += d*dt
+    const float x = __half2float(lat[i]);
+    const float ef = __half2float(e);
+    const float pred = x - sigma * ef;
+    const float deriv = (x - pred) / sigma;
+    const __half xn = __float2half_rn(x + deriv * (sigma_next - sigma));
+    lat[i] = xn;
+    if (next_in) {
+      const __half scaled = __float2half_rn(__half2float(xn) / sqrtf(sigma_next * sigma_next + 1.f));
+      next_in[(size_t)p * in_ld + c] = scaled;
+      next_in[((size_t)HW + p) * in_ld + c] = scaled;
+    }
+  }
+}
+SS_API int ss_cfg_euler_step_f16(const void* eps, int eps_ld, void* latents, void* next_in, int in_ld, int HW, int C,
+                                 float guidance, float sigma, float sigma_next, void* stream) {
+  cfg_euler_kernel<<<ew_grid((long long)HW * C), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __half*)eps, eps_ld, (__half*)latents, (__half*)next_in, in_ld, HW, C, guidance, sigma, sigma_next);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- generic casts / scale: y = T2(x * scale) ------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void cast_scale_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = ss_num<TO>::from_f(ss_num<TI>::to_f(x[i]) * scale);
+}
+SS_API int ss_cast_scale(int dtype_in, const void* x, int dtype_out, void* y, long long n, float scale, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = ew_grid(n);
+  if (dtype_in == SS_F16 && dtype_out == SS_BF16)
+    cast_scale_kernel<__half, __nv_bfloat16><<<g, EW_THREADS, 0, s>>>((const __half*)x, (__nv_bfloat16*)y, n, scale);
+  else if (dtype_in == SS_BF16 && dtype_out == SS_F16)
+    cast_scale_kernel<__nv_bfloat16, __half><<<g, EW_THREADS, 0, s>>>((const __nv_bfloat16*)x, (__half*)y, n, scale);
+  else if (dtype_in == SS_F16 && dtype_out == SS_F16)
+    cast_scale_kernel<__half, __half><<<g, EW_THREADS, 0, s>>>((const __half*)x, (__half*)y, n, scale);
+  else if (dtype_in == SS_BF16 && dtype_out == SS_BF16)
+    cast_scale_kernel<__nv_bfloat16, __nv_bfloat16><<<g, EW_THREADS, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+                                                                             n, scale);
+  else
+    SS_FAIL("unsupported cast");
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- row softmax (VAE mid-block attention scores), fp32 math, in place --------------------------------
+template <typename T>
+__global__ void softmax_rows_kernel(T* __restrict__ x, int ld, int n, float scale) {
+  __shared__ float red[32];
+  T* row = x + (size_t)blockIdx.x * ld;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, ss_num<T>::to_f(row[i]) * scale);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += __expf(ss_num<T>::to_f(row[i]) * scale - m);
+  s = block_sum(s, red);
+  const float inv = 1.f / s;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    row[i] = ss_num<T>::from_f(__expf(ss_num<T>::to_f(row[i]) * scale - m) * inv);
+}
+SS_API int ss_softmax_rows(int dtype, void* x, int ld, int rows, int n, float scale, void* stream) {
+  if (rows == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == SS_F16)
+    softmax_rows_kernel<__half><<<rows, 512, 0, s>>>((__half*)x, ld, n, scale);
+  else
+    softmax_rows_kernel<__nv_bfloat16><<<rows, 512, 0, s>>>((__nv_bfloat16*)x, ld, n, scale);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- 2-D transpose of 16-bit elements: y[c, r] = x[r, c] ---------------------------------------------
+__global__ void transpose_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int R, int C) {
+  __shared__ uint16_t tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[j][threadIdx.x] = x[(size_t)r * C + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) y[(size_t)c * R + r] = tile[threadIdx.x][j];
+  }
+}
+SS_API int ss_transpose_16b(const void* x, void* y, int R, int C, void* stream) {
+  dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)x, (uint16_t*)y, R, C);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- mean over tokens: y[b, :] = mean_t x[b, t, :]  (AttentionPool2d, resampler.py:92) ----------------
+__global__ void mean_tokens_kernel(const __half* __restrict__ x, __half* __restrict__ y, int T, int C) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += __half2float(x[((size_t)b * T + t) * C + c]);
+  y[(size_t)b * C + c] = __float2half_rn(s / (float)T);
+}
+SS_API int ss_mean_tokens_f16(const void* x, void* y, int B, int T, int C, void* stream) {
+  if (B == 0) return 0;
+  mean_tokens_kernel<<<dim3(ceil_div(C, 128), B), 128, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, T, C);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- VAE output -> uint8 HWC image: (x/2 + 0.5).clamp(0,1) * 255, round (diffusers VaeImageProcessor) ----
+template <typename T>
+__global__ void to_uint8_kernel(const T* __restrict__ x, int ldx, uint8_t* __restrict__ out, long long pixels, int C) {
+  const long long total = pixels * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / C;
+    const int c = (int)(i % C);
+    float v = ss_num<T>::to_f(x[p * ldx + c]) * 0.5f + 0.5f;
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    out[i] = (uint8_t)rintf(v * 255.f);
+  }
+}
+SS_API int ss_image_to_uint8(int dtype, const void* x, int ldx, void* out, long long pixels, int C, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == SS_F16)
+    to_uint8_kernel<__half><<<ew_grid(pixels * C), EW_THREADS, 0, s>>>((const __half*)x, ldx, (uint8_t*)out, pixels, C);
+  else
+    to_uint8_kernel<__nv_bfloat16><<<ew_grid(pixels * C), EW_THREADS, 0, s>>>((const __nv_bfloat16*)x, ldx,
+                                                                              (uint8_t*)out, pixels, C);
+  SS_LAUNCH_CHECK();
+  return 0;
+}

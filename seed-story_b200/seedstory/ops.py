@@ -159,3 +159,127 @@ def conv3x3(x, w, bias=None, bias2=None, residual=None, act=ACT_NONE, out=None, 
     _capi.call("ss_conv3x3_nhwc", _dt(x), _p(x), _p(w), _p(out), Nimg, H, W_, Cin, Cout, _p(bias), _p(bias2),
                _p(residual), act, force_bn, _stream())
     return out
+
+
+def fmha(q, k, v, out, B, H, Lq, Lk, D, q_strides, k_strides, v_strides, o_strides, scale, causal=False,
+         kv_lens=None, page_table=None):
+    """Strides are (batch, token, head) in elements; tensors may be views into fused buffers."""
+    _req_cuda(q, k, v, out)
+    LL = ctypes.c_longlong
+    args = [_p(q), _p(k), _p(v), _p(out), B, H, Lq, Lk, D]
+    for st in (q_strides, k_strides, v_strides, o_strides):
+        args += [LL(int(st[0])), LL(int(st[1])), LL(int(st[2]))]
+    args += [_p(kv_lens), _p(page_table), page_table.shape[1] if page_table is not None else 0,
+             ctypes.c_float(scale), 1 if causal else 0, _stream()]
+    _capi.call("ss_fmha_f16", *args)
+    return out
+
+
+def mha_packed(q, k, v, heads, scale, causal=False, out=None):
+    """q [B, Lq, heads*D], k/v [B, Lk, heads*D] (last dim contiguous; may be column slices of fused buffers)."""
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    D = E // heads
+    if out is None:
+        out = torch.empty((B, Lq, E), dtype=q.dtype, device=q.device)
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    return fmha(q, k, v, out, B, heads, Lq, Lk, D, (q.stride(0), q.stride(1), D), (k.stride(0), k.stride(1), D),
+                (v.stride(0), v.stride(1), D), (out.stride(0), out.stride(1), D), scale, causal)
+
+
+def im2col_patch(img, P, Kpad):
+    B, C, S, _ = img.shape
+    G = S // P
+    out = torch.empty((B * G * G, Kpad), dtype=img.dtype, device=img.device)
+    _capi.call("ss_im2col_patch_f16", _p(img.contiguous()), _p(out), B, C, S, P, Kpad, _stream())
+    return out
+
+
+def add_bcast(x, add, out=None):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out = torch.empty_like(x) if out is None else out
+    _capi.call("ss_add_bcast", _dt(x), _p(x), _p(add), _p(out), ctypes.c_longlong(rows), C, add.numel() // C,
+               _stream())
+    return out
+
+
+def scatter_rows(src, dst_rows, dst):
+    _capi.call("ss_scatter_rows_16b", _p(src), _p(dst_rows), _p(dst), dst.stride(0), src.shape[0], src.shape[1],
+               _stream())
+
+
+def groupnorm_nhwc(x, gamma, beta, groups, eps, silu, stats_ws, out=None):
+    N, H, W, C = x.shape
+    out = torch.empty_like(x) if out is None else out
+    _capi.call("ss_groupnorm_nhwc", _dt(x), _p(x), _p(out), _p(gamma), _p(beta), _p(stats_ws), N, H * W, C, groups,
+               ctypes.c_float(eps), 1 if silu else 0, _stream())
+    return out
+
+
+def upsample2x(x, out=None):
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, 2 * H, 2 * W, C), dtype=x.dtype, device=x.device)
+    _capi.call("ss_upsample2x_nhwc_16b", _p(x), _p(out), N, H, W, C, _stream())
+    return out
+
+
+def concat_channels(a, b, out=None):
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    rows = a.numel() // Ca
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (Ca + Cb,), dtype=a.dtype, device=a.device)
+    _capi.call("ss_concat_channels_16b", _p(a), _p(b), _p(out), ctypes.c_longlong(rows), Ca, Cb, _stream())
+    return out
+
+
+def im2col3x3_s2(x, out=None):
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N * (H // 2) * (W // 2), 9 * C), dtype=x.dtype, device=x.device)
+    _capi.call("ss_im2col3x3_s2_nhwc_16b", _p(x), _p(out), N, H, W, C, _stream())
+    return out
+
+
+def cfg_euler_step(eps, latents, next_in, C, guidance, sigma, sigma_next):
+    """eps [2, HW, Cpad] fp16; latents [HW, C] fp16 updated in place; next_in [2, HW, Cin_pad] or None."""
+    HW = latents.shape[0]
+    _capi.call("ss_cfg_euler_step_f16", _p(eps), eps.shape[-1], _p(latents), _p(next_in),
+               next_in.shape[-1] if next_in is not None else 0, HW, C, ctypes.c_float(guidance),
+               ctypes.c_float(sigma), ctypes.c_float(sigma_next), _stream())
+
+
+def cast_scale(x, out_dtype, scale=1.0, out=None):
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device) if out is None else out
+    _capi.call("ss_cast_scale", _dt(x), _p(x), _dt(out), _p(out), ctypes.c_longlong(x.numel()),
+               ctypes.c_float(scale), _stream())
+    return out
+
+
+def softmax_rows_(x, scale=1.0):
+    rows, n = x.shape
+    _capi.call("ss_softmax_rows", _dt(x), _p(x), x.stride(0), rows, n, ctypes.c_float(scale), _stream())
+    return x
+
+
+def transpose2d(x, out=None):
+    R, C = x.shape
+    out = torch.empty((C, R), dtype=x.dtype, device=x.device) if out is None else out
+    _capi.call("ss_transpose_16b", _p(x), _p(out), R, C, _stream())
+    return out
+
+
+def mean_tokens(x):
+    B, T, C = x.shape
+    y = torch.empty((B, C), dtype=x.dtype, device=x.device)
+    _capi.call("ss_mean_tokens_f16", _p(x.contiguous()), _p(y), B, T, C, _stream())
+    return y
+
+
+def image_to_uint8(x, C):
+    """x [pixels, ld] (first C channels valid) -> uint8 [pixels, C]."""
+    pixels = x.shape[0]
+    out = torch.empty((pixels, C), dtype=torch.uint8, device=x.device)
+    _capi.call("ss_image_to_uint8", _dt(x), _p(x), x.stride(0), _p(out), ctypes.c_longlong(pixels), C, _stream())
+    return out

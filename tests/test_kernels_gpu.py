@@ -26,7 +26,7 @@ def test_rmsnorm(cuda_dev):
         y = ops.rmsnorm(x, w, 1e-5)
         var = x.float().pow(2).mean(-1, keepdim=True)
         ref = w * (x * torch.rsqrt(var + 1e-5)).half()
-        _close(y, ref, rtol=1e-3, atol=1e-3, what=f"rmsnorm {rows}x{K}")
+        _close(y, ref, rtol=2e-3, atol=1e-3, what=f"rmsnorm {rows}x{K}")  # 1 fp16 ulp
 
 
 def test_layernorm(cuda_dev):
@@ -226,3 +226,137 @@ def test_conv3x3(cuda_dev, dt):
         y = ops.conv3x3(x_nhwc, w_p, bias=bias, bias2=temb, residual=res)
         ref2 = (ref.to(dt).float() + temb.float()[:, :, None, None]).to(dt).float() + res.permute(0, 3, 1, 2).float()
         _close(y.permute(0, 3, 1, 2), ref2, rtol=tol, atol=tol * ref2.abs().max().item(), what="conv+temb+res")
+
+
+def _ref_attn(q, k, v, scale, causal):
+    # q [B,Lq,H,D] etc, fp32 math
+    q, k, v = q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)
+    s = q @ k.transpose(-1, -2) * scale
+    if causal:
+        tq, tk = q.shape[-2], k.shape[-2]
+        qi = torch.arange(tq, device=q.device)[:, None]
+        kj = torch.arange(tk, device=q.device)[None, :]
+        s = s.masked_fill(~(kj <= qi + (tk - tq)), float("-inf"))
+    return (torch.softmax(s, -1) @ v).transpose(1, 2)
+
+
+@pytest.mark.parametrize("D", [64, 128])
+def test_fmha_dense(cuda_dev, D):
+    from seedstory import ops
+    torch.manual_seed(6)
+    for (B, H, Lq, Lk, causal) in [(2, 4, 64, 64, False), (1, 3, 100, 333, False), (2, 2, 257, 257, True),
+                                   (1, 2, 66, 1107, True), (1, 16, 1024, 1024, False), (2, 2, 64, 320, False)]:
+        # fused qkv buffer for self-attention shapes, separate buffers otherwise
+        q = torch.randn(B, Lq, H, D, device=cuda_dev).half()
+        k = torch.randn(B, Lk, H, D, device=cuda_dev).half()
+        v = torch.randn(B, Lk, H, D, device=cuda_dev).half()
+        scale = 1.0 / math.sqrt(D)
+        out = ops.mha_packed(q.view(B, Lq, H * D), k.view(B, Lk, H * D), v.view(B, Lk, H * D), H, scale, causal)
+        ref = _ref_attn(q, k, v, scale, causal)
+        _close(out.view(B, Lq, H, D), ref, rtol=3e-3, atol=3e-3, what=f"fmha D={D} {B},{H},{Lq},{Lk},{causal}")
+    # strided views into one fused [B, L, 3*H*D] buffer
+    B, H, L = 2, 4, 200
+    qkv = torch.randn(B, L, 3 * H * D, device=cuda_dev).half()
+    q, k, v = qkv[..., :H * D], qkv[..., H * D:2 * H * D], qkv[..., 2 * H * D:]
+    out = ops.mha_packed(q, k, v, H, 0.1)
+    ref = _ref_attn(q.reshape(B, L, H, D), k.reshape(B, L, H, D), v.reshape(B, L, H, D), 0.1, False)
+    _close(out.view(B, L, H, D), ref, rtol=3e-3, atol=3e-3, what="fmha fused-qkv views")
+
+
+def test_fmha_paged_causal(cuda_dev):
+    from seedstory import ops
+    torch.manual_seed(7)
+    H, D = 32, 128
+    Lk, Lq = 1107, 66
+    max_pages = 24
+    pool = torch.randn(40, H, 64, D, device=cuda_dev).half()
+    vpool = torch.randn(40, H, 64, D, device=cuda_dev).half()
+    pt = torch.randperm(40, device=cuda_dev)[:max_pages].int().view(1, max_pages).contiguous()
+    q = torch.randn(1, Lq, H * D, device=cuda_dev).half()
+    out = torch.empty_like(q)
+    ops.fmha(q, pool, vpool, out, 1, H, Lq, Lk, D, (0, H * D, D), (0, 0, 0), (0, 0, 0), (0, H * D, D),
+             1.0 / math.sqrt(D), causal=True, page_table=pt)
+    npg = (Lk + 63) // 64
+    k = pool[pt[0, :npg].long()].permute(0, 2, 1, 3).reshape(-1, H, D)[:Lk][None]
+    v = vpool[pt[0, :npg].long()].permute(0, 2, 1, 3).reshape(-1, H, D)[:Lk][None]
+    ref = _ref_attn(q.view(1, Lq, H, D), k, v, 1.0 / math.sqrt(D), True)
+    _close(out.view(1, Lq, H, D), ref, rtol=3e-3, atol=3e-3, what="fmha paged causal")
+
+
+def test_groupnorm_and_glue(cuda_dev):
+    from seedstory import ops
+    torch.manual_seed(8)
+    for dt, tol in ((torch.float16, 4e-3), (torch.bfloat16, 3e-2)):
+        for (N, H, W, C) in [(2, 32, 32, 320), (1, 64, 64, 640), (2, 16, 16, 2560), (1, 128, 128, 128)]:
+            x = (torch.randn(N, H, W, C, device=cuda_dev) * 2 + 0.5).to(dt)
+            g = (1 + 0.1 * torch.randn(C, device=cuda_dev)).to(dt)
+            b = (0.1 * torch.randn(C, device=cuda_dev)).to(dt)
+            ws = torch.empty(2 * N * 32, device=cuda_dev, dtype=torch.float32)
+            for silu in (False, True):
+                y = ops.groupnorm_nhwc(x, g, b, 32, 1e-5, silu, ws)
+                ref = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), 32, g.float(), b.float(), 1e-5)
+                if silu:
+                    ref = torch.nn.functional.silu(ref.to(dt).float())
+                _close(y.permute(0, 3, 1, 2), ref, rtol=tol, atol=tol, what=f"groupnorm {N},{H},{W},{C} silu={silu} {dt}")
+    x = torch.randn(2, 8, 8, 64, device=cuda_dev).half()
+    up = ops.upsample2x(x)
+    ref = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest")
+    assert torch.equal(up.permute(0, 3, 1, 2).float(), ref)
+    a = torch.randn(2, 8, 8, 64, device=cuda_dev).half()
+    b = torch.randn(2, 8, 8, 128, device=cuda_dev).half()
+    assert torch.equal(ops.concat_channels(a, b), torch.cat([a, b], -1))
+    # stride-2 conv through im2col + GEMM
+    Cin, Cout = 64, 128
+    xi = torch.randn(2, Cin, 32, 32, device=cuda_dev).half()
+    w = (torch.randn(Cout, Cin, 3, 3, device=cuda_dev) / math.sqrt(9 * Cin)).half()
+    bias = torch.randn(Cout, device=cuda_dev).half()
+    cols = ops.im2col3x3_s2(xi.permute(0, 2, 3, 1).contiguous())
+    y = ops.gemm(cols, w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous(), bias=bias)
+    ref = torch.nn.functional.conv2d(xi.float(), w.float(), bias.float(), stride=2, padding=1)
+    _close(y.view(2, 16, 16, Cout).permute(0, 3, 1, 2), ref, rtol=3e-3, atol=3e-3 * ref.abs().max().item(), what="conv s2")
+    # patchify
+    img = torch.randn(2, 3, 56, 56, device=cuda_dev).half()
+    pat = ops.im2col_patch(img, 14, 640)
+    ref = torch.nn.functional.unfold(img.float(), 14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert torch.equal(pat[:, :588].float(), ref) and pat[:, 588:].abs().max().item() == 0
+    # softmax rows / transpose / mean / l2norm / scatter / add_bcast / cast / uint8
+    s = torch.randn(37, 1000, device=cuda_dev).half()
+    ref = torch.softmax(s.float() * 0.3, -1)
+    _close(ops.softmax_rows_(s.clone(), 0.3), ref, rtol=2e-3, atol=1e-5, what="softmax rows")
+    t = torch.randn(70, 130, device=cuda_dev).half()
+    assert torch.equal(ops.transpose2d(t), t.t().contiguous())
+    m = torch.randn(2, 64, 256, device=cuda_dev).half()
+    _close(ops.mean_tokens(m), m.float().mean(1), rtol=2e-3, atol=1e-3, what="mean tokens")
+    _close(ops.l2norm_tokens(m), torch.nn.functional.normalize(m.float(), dim=1), rtol=3e-3, atol=1e-4, what="l2norm")
+    dst = torch.zeros(50, 128, device=cuda_dev).half()
+    src = torch.randn(5, 128, device=cuda_dev).half()
+    rows = torch.tensor([3, 9, 10, 49, 0], device=cuda_dev, dtype=torch.int32)
+    ops.scatter_rows(src, rows, dst)
+    assert torch.equal(dst[rows.long()], src)
+    xx = torch.randn(6, 4, 64, device=cuda_dev).half()
+    pe = torch.randn(4, 64, device=cuda_dev).half()
+    assert torch.equal(ops.add_bcast(xx, pe), xx + pe)
+    assert torch.equal(ops.cast_scale(xx, torch.bfloat16, 2.0), (xx.float() * 2).bfloat16())
+    im = torch.randn(100, 8, device=cuda_dev).half()
+    u8 = ops.image_to_uint8(im, 3)
+    ref = ((im[:, :3].float() / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)
+    assert (u8.int() - ref.int()).abs().max().item() <= 1
+
+
+def test_cfg_euler_step(cuda_dev):
+    from seedstory import ops
+    torch.manual_seed(9)
+    HW, C = 128 * 128, 4
+    eps = torch.randn(2, HW, 8, device=cuda_dev).half()
+    lat = torch.randn(HW, C, device=cuda_dev).half()
+    nxt = torch.zeros(2, HW, 64, device=cuda_dev).half()
+    sigma, sigma_next, g = 14.6, 11.2, 7.5
+    eu, ec = eps[0, :, :C], eps[1, :, :C]
+    e = eu + (g * (ec - eu))
+    x = lat.float()
+    pred = x - sigma * e.float()
+    ref = (x + (x - pred) / sigma * (sigma_next - sigma)).half()
+    ops.cfg_euler_step(eps, lat, nxt, C, g, sigma, sigma_next)
+    _close(lat, ref, rtol=2e-3, atol=2e-2, what="euler")
+    _close(nxt[1, :, :C], ref.float() / math.sqrt(sigma_next ** 2 + 1), rtol=2e-3, atol=2e-3, what="scaled input")
+    assert nxt[:, :, C:].abs().max().item() == 0
