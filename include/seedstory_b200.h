@@ -77,7 +77,15 @@ SS_EXPORT int ss_gather_rows_16b(const void* table, const int* ids, void* out, i
 /* greedy-loop bookkeeping on the device (append id, advance position/slot/length, EOS -> done) —
  * restates the sequence/position updates of HF greedy_search + prepare_inputs_for_generation (:827-844) */
 SS_EXPORT int ss_decode_advance(const int* next_ids, int* cur_ids, int* tok_pos, int* tok_slot, int* seq_lens,
-                                int* out_ids, int out_cap, int* n_out, int* done, int eos_id, int B, void* stream);
+                                int* out_ids, int out_cap, int* n_out, int* done, int eos_id, int B,
+                                const int* schedule, int sched_cap, void* stream);
+/* keep the step's post-final-norm hidden row (src/models_clm/models.py:182-197 slices them afterwards) */
+SS_EXPORT int ss_store_rows_indexed_16b(const void* src, int ld_src, void* dst, int cap, const int* idx, int B,
+                                        int width, void* stream);
+/* peft 0.4 LoRA Linear folded into the base weight: W' = W + (alpha/r) B A, fp32 accumulate, one rounding
+ * (configs/clm_models/llama2chat7b_lora.yaml:7-27; wrap at src/models_clm/peft_models.py:49) */
+SS_EXPORT int ss_lora_merge_f16(const void* W, const void* A, const void* B, void* out, int N, int K, int r,
+                                float scaling, void* stream);
 
 /* ---- dense contractions on tcgen05 ------------------------------------------------------------ */
 /* C[M,N] = epi(alpha * A[M,K] B[N,K]^T): every nn.Linear on the prefill / ViT / resampler / UNet /
@@ -93,8 +101,8 @@ SS_EXPORT int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int l
  * conv1/conv2, Up/Downsample convs, VAE decoder convs — SURVEY.md Appendix C).  w is [Cout, 9*Cin] with
  * k = (ky*3+kx)*Cin + c.  bias2 is the per-image time-embedding row [Nimg, Cout]. */
 SS_EXPORT int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin,
-                              int Cout, const void* bias, const void* bias2, const void* residual, int act,
-                              int force_bn, void* stream);
+                              int Cout, const void* bias, const void* bias2, int ld_bias2, const void* residual,
+                              int act, int force_bn, void* stream);
 
 /* ---- fused attention ---------------------------------------------------------------------------- */
 /* softmax(scale * Q K^T [+ bottom-right causal mask]) V, fp16, head_dim 64/128, explicit (batch, token, head)
@@ -133,6 +141,8 @@ SS_EXPORT int ss_im2col3x3_s2_nhwc_16b(const void* x, void* cols, int N, int H, 
  * the per-step glue of StableDiffusionXLPipeline.__call__ reached from src/models_ipa/adapter_modules.py:455-466 */
 SS_EXPORT int ss_cfg_euler_step_f16(const void* eps, int eps_ld, void* latents, void* next_in, int in_ld, int HW,
                                     int C, float guidance, float sigma, float sigma_next, void* stream);
+/* y = act(x) elementwise: 1 gelu(erf), 2 silu (e.g. the SiLU before ResnetBlock2D.time_emb_proj) */
+SS_EXPORT int ss_unary(int dtype, const void* x, void* y, long long n, int op, void* stream);
 SS_EXPORT int ss_cast_scale(int dtype_in, const void* x, int dtype_out, void* y, long long n, float scale,
                             void* stream);
 /* in-place softmax(scale * row) — VAE mid-block single-head attention over 16384 tokens */

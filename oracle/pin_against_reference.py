@@ -73,7 +73,7 @@ def pin_llama():
     sys.path.insert(0, REF)
     from src.models_clm import modeling_llama_xformer as M  # the reference file itself
     from transformers import LlamaConfig
-    hidden, inter, heads, layers, vocab = 128, 352, 4, 3, 320
+    hidden, inter, heads, layers, vocab = 256, 352, 2, 3, 320  # head_dim 128 like Llama-2-7B
     cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads,
                       num_hidden_layers=layers, vocab_size=vocab, rms_norm_eps=1e-5, max_position_embeddings=512,
                       pad_token_id=0)
@@ -177,7 +177,7 @@ def pin_vision():
         torch.save({"sd": rs.state_dict(), "x": x, "out": ref, "grid": grid, "heads": 2},
                    os.path.join(GOLD, f"{name}.pt"))
 
-    xl = RS.ResamplerXLV2(dim=128, depth=2, dim_head=32, heads=4, num_queries=16, embedding_dim=256, output1_dim=96,
+    xl = RS.ResamplerXLV2(dim=256, depth=2, dim_head=64, heads=4, num_queries=16, embedding_dim=256, output1_dim=96,
                           output2_dim=160, ff_mult=4).eval()
     x = torch.randn(2, 64, 256)
     with torch.no_grad():
@@ -187,7 +187,7 @@ def pin_vision():
     assert d < 1e-4, d
     print("ResamplerXLV2 pinned: max diff", d)
     torch.save({"sd": xl.state_dict(), "x": x, "out1": r1, "out2": r2,
-                "cfg": dict(dim=128, depth=2, dim_head=32, heads=4, num_queries=16, embedding_dim=256,
+                "cfg": dict(dim=256, depth=2, dim_head=64, heads=4, num_queries=16, embedding_dim=256,
                             output1_dim=96, output2_dim=160, ff_mult=4)}, os.path.join(GOLD, "resampler_xlv2.pt"))
 
 

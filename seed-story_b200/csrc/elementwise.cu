@@ -417,3 +417,22 @@ SS_API int ss_image_to_uint8(int dtype, const void* x, int ldx, void* out, long 
   SS_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- y = act(x) -----------------------------------------------------------------------------------
+template <typename T>
+__global__ void unary_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int op) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = ss_num<T>::to_f(x[i]);
+    y[i] = ss_num<T>::from_f(op == 1 ? gelu_erf(v) : v / (1.f + expf(-v)));
+  }
+}
+SS_API int ss_unary(int dtype, const void* x, void* y, long long n, int op, void* stream) {
+  SS_REQUIRE(op == 1 || op == 2, "op: 1 gelu, 2 silu");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == SS_F16)
+    unary_kernel<__half><<<ew_grid(n), EW_THREADS, 0, s>>>((const __half*)x, (__half*)y, n, op);
+  else
+    unary_kernel<__nv_bfloat16><<<ew_grid(n), EW_THREADS, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, op);
+  SS_LAUNCH_CHECK();
+  return 0;
+}

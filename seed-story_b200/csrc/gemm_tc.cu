@@ -25,8 +25,9 @@ struct GemmParams {
   void* out;
   int ldo;
   const void* bias;      // [N] or null
-  const void* bias2;     // [groups, N] or null; group = row / rows_per_group
+  const void* bias2;     // [groups, ld_b2] or null; group = row / rows_per_group
   int rows_per_group;
+  int ld_b2;
   const void* residual;  // [M, ldr] or null
   int ldr;
   int act;  // 0 none, 1 gelu(erf), 2 silu
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
     T* out_row = reinterpret_cast<T*>(p.out) + m * p.ldo;
     const T* res_row = p.residual ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
     const T* b2_row =
-        p.bias2 ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.N : nullptr;
+        p.bias2 ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2 : nullptr;
 
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -391,6 +392,7 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
   p.bias = bias;
   p.bias2 = bias2;
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  p.ld_b2 = N;
   p.residual = residual;
   p.ldr = ldr;
   p.act = act;
@@ -406,8 +408,8 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
 // 3x3 stride-1 pad-1 convolution, NHWC activations [Nimg,H,W,Cin], weights [Cout, 9*Cin] with
 // k = (ky*3+kx)*Cin + c, output NHWC [Nimg,H,W,Cout].
 SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout,
-                           const void* bias, const void* bias2 /*[Nimg,Cout]*/, const void* residual, int act,
-                           int force_bn, void* stream) {
+                           const void* bias, const void* bias2 /*[Nimg, ld_bias2]*/, int ld_bias2,
+                           const void* residual, int act, int force_bn, void* stream) {
   SS_REQUIRE(dtype == SS_F16 || dtype == SS_BF16, "dtype must be f16 or bf16");
   SS_REQUIRE(Cin % BK == 0, "Cin must be a multiple of 64 for the tensor-core conv");
   SS_REQUIRE(Cout % 8 == 0, "Cout must be a multiple of 8");
@@ -434,6 +436,7 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
   p.bias = bias;
   p.bias2 = bias2;
   p.rows_per_group = H * W;
+  p.ld_b2 = ld_bias2 > 0 ? ld_bias2 : Cout;
   p.residual = residual;
   p.ldr = Cout;
   p.act = act;

@@ -440,12 +440,17 @@ SS_API int ss_gather_rows_16b(const void* table, const int* ids, void* out, int 
 __global__ void decode_advance_kernel(const int* __restrict__ next_ids, int* __restrict__ cur_ids,
                                       int* __restrict__ tok_pos, int* __restrict__ tok_slot,
                                       int* __restrict__ seq_lens, int* __restrict__ out_ids, int out_cap,
-                                      int* __restrict__ n_out, int* __restrict__ done, int eos_id, int B) {
+                                      int* __restrict__ n_out, int* __restrict__ done, int eos_id, int B,
+                                      const int* __restrict__ schedule, int sched_cap) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   if (done[b]) return;
-  const int id = next_ids[b];
+  int id = next_ids[b];
   const int k = n_out[b];
+  // optional forced schedule (the reference exposes the same hook as `logits_processor=`, models.py:105,115):
+  // entry >= 0 overrides the greedy choice for generated index k (used to force <img>/EOS with synthetic weights)
+  if (schedule != nullptr && k < sched_cap && schedule[(size_t)b * sched_cap + k] >= 0)
+    id = schedule[(size_t)b * sched_cap + k];
   if (k < out_cap) out_ids[(size_t)b * out_cap + k] = id;
   n_out[b] = k + 1;
   cur_ids[b] = id;
@@ -456,10 +461,56 @@ __global__ void decode_advance_kernel(const int* __restrict__ next_ids, int* __r
 }
 
 SS_API int ss_decode_advance(const int* next_ids, int* cur_ids, int* tok_pos, int* tok_slot, int* seq_lens,
-                             int* out_ids, int out_cap, int* n_out, int* done, int eos_id, int B, void* stream) {
+                             int* out_ids, int out_cap, int* n_out, int* done, int eos_id, int B,
+                             const int* schedule, int sched_cap, void* stream) {
   if (B == 0) return 0;
+  SS_REQUIRE(B <= 32, "at most 32 sequences per rank");
   decode_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(next_ids, cur_ids, tok_pos, tok_slot, seq_lens, out_ids,
-                                                            out_cap, n_out, done, eos_id, B);
+                                                            out_cap, n_out, done, eos_id, B, schedule, sched_cap);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// dst[b, idx[b], :] = src[b, :] with a device-side row index (keeps the per-step final-norm hidden state that
+// ContinuousLVLM.generate slices at models.py:182-197 while the decode step stays CUDA-graph replayable).
+__global__ void store_rows_indexed_kernel(const uint16_t* __restrict__ src, int ld_src, uint16_t* __restrict__ dst,
+                                          int cap, const int* __restrict__ idx, int width) {
+  const int b = blockIdx.x;
+  const int r = idx[b];
+  if (r < 0 || r >= cap) return;
+  const vec8* s = reinterpret_cast<const vec8*>(src + (size_t)b * ld_src);
+  vec8* d = reinterpret_cast<vec8*>(dst + ((size_t)b * cap + r) * width);
+  for (int v = threadIdx.x; v < (width >> 3); v += blockDim.x) d[v] = s[v];
+}
+SS_API int ss_store_rows_indexed_16b(const void* src, int ld_src, void* dst, int cap, const int* idx, int B, int width,
+                                     void* stream) {
+  SS_REQUIRE(width % 8 == 0 && ld_src % 8 == 0, "width % 8");
+  if (B == 0) return 0;
+  store_rows_indexed_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, ld_src, (uint16_t*)dst, cap, idx,
+                                                                width);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+// W' = W + scaling * B A  (peft LoRA merge: fp32 accumulate, ONE rounding to fp16 — SURVEY.md §7 "LoRA").
+__global__ void lora_merge_kernel(const __half* __restrict__ W, const __half* __restrict__ A,
+                                  const __half* __restrict__ Bm, __half* __restrict__ out, int N, int K, int r,
+                                  float scaling) {
+  extern __shared__ float brow[];  // B[n, :] for this row
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < r; i += blockDim.x) brow[i] = __half2float(Bm[(size_t)n * r + i]);
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < r; ++i) acc += brow[i] * __half2float(A[(size_t)i * K + k]);
+    out[(size_t)n * K + k] = __float2half_rn(__half2float(W[(size_t)n * K + k]) + scaling * acc);
+  }
+}
+SS_API int ss_lora_merge_f16(const void* W, const void* A, const void* B, void* out, int N, int K, int r,
+                             float scaling, void* stream) {
+  if (N == 0) return 0;
+  lora_merge_kernel<<<N, 256, r * sizeof(float), (cudaStream_t)stream>>>((const __half*)W, (const __half*)A,
+                                                                        (const __half*)B, (__half*)out, N, K, r, scaling);
   SS_LAUNCH_CHECK();
   return 0;
 }

@@ -42,10 +42,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (reported as a launch failure) instead of a hung GPU.
+// try_wait itself may block for a hardware-defined interval, so the bound is on wall-clock time (2 s).
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (globaltimer_ns() - t0 > 2000000000ull) {
       printf("seedstory_b200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }

@@ -76,5 +76,23 @@ def check(rc):
         raise SeedStoryError(lib().ss_last_error().decode())
 
 
+# kernels launched per C-ABI call (everything else launches exactly one); used for bench.py's `gpu_launches`
+_KERNELS_PER_CALL = {"ss_attn_decode_paged_f16": 2, "ss_groupnorm_nhwc": 2, "ss_last_error": 0, "ss_version": 0,
+                     "ss_require_device": 0, "ss_stream_sync": 0}
+_launches = 0
+
+
+def launch_count():
+    return _launches
+
+
+def add_launches(n):
+    """CUDA-graph replays re-issue the kernels recorded at capture time without passing through call()."""
+    global _launches
+    _launches += n
+
+
 def call(name, *args):
+    global _launches
     check(getattr(lib(), name)(*args))
+    _launches += _KERNELS_PER_CALL.get(name, 1)

@@ -1,0 +1,355 @@
+"""Llama-2 decode/prefill engine over the seedstory_b200 kernels (host side: buffers, page tables, launches).
+
+Replaces, for inference, the arithmetic of the reference's
+  src/models_clm/modeling_llama_xformer.py  LlamaModel.forward :532-666, LlamaDecoderLayer :318-368,
+                                            LlamaAttention :217-301, lm_head :759,
+                                            prepare_inputs_for_generation :796-852 (position rule)
+  transformers 4.34 greedy_search (call site src/models_clm/models.py:146-153)
+  src/models_clm/generation.py:19-31        (logits processor, fused with the argmax on the device)
+  peft 0.4 LoRA Linear                      (folded into the base weights once at load)
+
+Data layout in HBM
+  weights   per layer: qkv [3*hid, hid] (q|k|v rows), o [hid, hid], gate_up [2*inter, hid] with rows
+            interleaved (gate_j, up_j), down [hid, inter]; fp16, LoRA merged (fp32 accumulate, one rounding)
+  KV cache  k_pages/v_pages [layers, pages, heads, 64, head_dim] fp16; a sequence owns an ordered list of
+            pages (page table row); sink compaction copies retained tokens into fresh pages
+  decode    every per-step scalar (ids, positions, slots, lengths, done flags) lives on the device so one
+            decode step is a single CUDA-graph replay with no host round trip except the 4-byte id read.
+"""
+import math
+
+import torch
+
+from . import _capi, ops
+
+PAGE = ops.KV_PAGE
+
+
+class LlamaConfig:
+    def __init__(self, hidden=4096, inter=11008, heads=32, layers=32, vocab=32066, eps=1e-5, max_pos=4096):
+        self.hidden, self.inter, self.heads, self.layers, self.vocab, self.eps, self.max_pos = \
+            hidden, inter, heads, layers, vocab, eps, max_pos
+        self.head_dim = hidden // heads
+
+
+def rope_tables_f16(head_dim, n_pos, device, base=10000.0):
+    """fp32 tables as the reference builds them (modeling_llama_xformer.py:120-137), cast to fp16 (:150-151).
+    Constant precompute on the host at load time."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2).float() / head_dim))
+    t = torch.arange(n_pos, dtype=inv_freq.dtype)
+    freqs = torch.einsum("i,j->ij", t, inv_freq)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().half().to(device), emb.sin().half().to(device)
+
+
+class LlamaEngine:
+    def __init__(self, cfg, device, max_batch=1, max_ctx=4096, max_new=512, decode_splits=8):
+        ops.require_device()
+        self.cfg, self.dev = cfg, device
+        self.max_batch = max_batch
+        self.max_pages = (max_ctx + PAGE - 1) // PAGE
+        self.max_new = max_new
+        self.splits = max(decode_splits, (self.max_pages * PAGE + 1023) // 1024)
+        c = cfg
+        assert c.head_dim == 128, "attention kernels are specialised for head_dim 128"
+        self.w = None
+        n_pages = max_batch * self.max_pages + 8
+        self.k_pages = torch.zeros((c.layers, n_pages, c.heads, PAGE, c.head_dim), dtype=torch.float16, device=device)
+        self.v_pages = torch.zeros_like(self.k_pages)
+        self.free_pages = list(range(n_pages))
+        self.page_table_h = torch.zeros((max_batch, self.max_pages), dtype=torch.int32)
+        self.page_table = torch.zeros((max_batch, self.max_pages), dtype=torch.int32, device=device)
+        self.n_pages_owned = [0] * max_batch
+        self.seq_len_h = [0] * max_batch
+        self.cos, self.sin = rope_tables_f16(c.head_dim, c.max_pos, device)
+        i32 = dict(dtype=torch.int32, device=device)
+        B = max_batch
+        # decode state (device resident)
+        self.cur_ids = torch.zeros(B, **i32)
+        self.next_ids = torch.zeros(B, **i32)
+        self.tok_pos = torch.zeros(B, **i32)
+        self.tok_slot = torch.zeros(B, **i32)
+        self.seq_lens = torch.zeros(B, **i32)
+        self.tok_seq = torch.arange(B, **i32)
+        self.n_out = torch.zeros(B, **i32)
+        self.done = torch.zeros(B, **i32)
+        self.out_ids = torch.zeros((B, max_new), **i32)
+        self.schedule = torch.full((B, max_new), -1, **i32)
+        self.hist = torch.zeros((B, max_new, c.hidden), dtype=torch.float16, device=device)
+        f16 = dict(dtype=torch.float16, device=device)
+        self.d_h = torch.zeros((B, c.hidden), **f16)
+        self.d_xn = torch.zeros((B, c.hidden), **f16)
+        self.d_qkv = torch.zeros((B, 3 * c.hidden), **f16)
+        self.d_q = torch.zeros((B, c.hidden), **f16)
+        self.d_attn = torch.zeros((B, c.hidden), **f16)
+        self.d_act = torch.zeros((B, c.inter), **f16)
+        self.d_logits = torch.zeros((B, c.vocab), **f16)
+        self.d_ws = torch.zeros(B * c.heads * self.splits * (c.head_dim + 2), dtype=torch.float32, device=device)
+        self.img_ids = None
+        self.eos_id = 2
+        self._graphs = {}
+        self._pinned_ids = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self._pinned_done = torch.zeros(B, dtype=torch.int32).pin_memory()
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, embed, layers, norm, lm_head, lora_scaling=2.0):
+        """`layers`: list of dicts with q_proj..down_proj [out,in] fp16 (+ optional '<name>.lora_A' [r,in],
+        '<name>.lora_B' [out,r]), input_layernorm, post_attention_layernorm.  Packs into kernel layouts."""
+        def merged(L, n):
+            W = L[n].to(self.dev, torch.float16).contiguous()
+            if n + ".lora_A" in L:
+                W = ops.lora_merge(W, L[n + ".lora_A"].to(self.dev, torch.float16),
+                                   L[n + ".lora_B"].to(self.dev, torch.float16), lora_scaling)
+            return W
+        packed = []
+        for L in layers:
+            q, k, v = merged(L, "q_proj"), merged(L, "k_proj"), merged(L, "v_proj")
+            g, u = merged(L, "gate_proj"), merged(L, "up_proj")
+            packed.append(dict(
+                qkv=torch.cat([q, k, v], 0).contiguous(),
+                o=merged(L, "o_proj"),
+                gate_up=torch.stack([g, u], dim=1).reshape(2 * g.shape[0], g.shape[1]).contiguous(),
+                down=merged(L, "down_proj"),
+                ln1=L["input_layernorm"].to(self.dev, torch.float16).contiguous(),
+                ln2=L["post_attention_layernorm"].to(self.dev, torch.float16).contiguous()))
+            del q, k, v, g, u
+        self.w = dict(layers=packed, embed=embed.to(self.dev, torch.float16).contiguous(),
+                      norm=norm.to(self.dev, torch.float16).contiguous(),
+                      lm_head=lm_head.to(self.dev, torch.float16).contiguous())
+        self._graphs.clear()
+
+    def set_image_token_ids(self, img_ids, eos_id=2):
+        """img_ids = [BOI, IMG_0..IMG_{n-1}, EOI] as produced by the reference processor's tokenizer.encode
+        (src/models_clm/generation.py:14-17)."""
+        self.img_ids = torch.tensor(list(img_ids), dtype=torch.int32, device=self.dev)
+        self.img_ids_h = list(img_ids)
+        self.eos_id = eos_id
+        self._graphs.clear()
+
+    def embed_tokens(self, ids):
+        ids = ids.to(self.dev, torch.int32).reshape(-1).contiguous()
+        out = torch.empty((ids.numel(), self.cfg.hidden), dtype=torch.float16, device=self.dev)
+        ops.gather_rows(self.w["embed"], ids, out)
+        return out
+
+    # ------------------------------------------------------------------ KV pages
+    def reset_sequence(self, b):
+        n = self.n_pages_owned[b]
+        self.free_pages.extend(self.page_table_h[b, :n].tolist())
+        self.n_pages_owned[b] = 0
+        self.seq_len_h[b] = 0
+
+    def _ensure_pages(self, b, n_tokens):
+        need = (n_tokens + PAGE - 1) // PAGE
+        assert need <= self.max_pages, f"sequence needs {need} pages > max {self.max_pages}"
+        changed = False
+        while self.n_pages_owned[b] < need:
+            self.page_table_h[b, self.n_pages_owned[b]] = self.free_pages.pop()
+            self.n_pages_owned[b] += 1
+            changed = True
+        if changed:
+            self.page_table[b].copy_(self.page_table_h[b], non_blocking=True)
+
+    # ------------------------------------------------------------------ prefill / chunk
+    def forward_chunk(self, b, embeds, positions, want_logits=True):
+        """Run T tokens of sequence b on top of its cache (prefill when the cache is empty).
+        embeds [T, hidden] fp16 device; positions: int tensor/list [T] (window-relative RoPE positions).
+        Returns (final-norm hidden [T, hidden], logits [1, vocab] of the last row or None)."""
+        c, w = self.cfg, self.w
+        T = embeds.shape[0]
+        base = self.seq_len_h[b]
+        self._ensure_pages(b, base + T)
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        pos = torch.as_tensor(positions, dtype=torch.int32).to(self.dev)
+        slot = torch.arange(base, base + T, **i32)
+        seq = torch.full((T,), b, **i32)
+        h = embeds.contiguous().clone()
+        q = torch.empty((T, c.hidden), dtype=torch.float16, device=self.dev)
+        attn = torch.empty_like(q)
+        xn = torch.empty_like(q)
+        qkv = torch.empty((T, 3 * c.hidden), dtype=torch.float16, device=self.dev)
+        act = torch.empty((T, c.inter), dtype=torch.float16, device=self.dev)
+        scale = 1.0 / math.sqrt(c.head_dim)
+        pt_row = self.page_table[b:b + 1]
+        Lk = base + T
+        for li, L in enumerate(w["layers"]):
+            ops.rmsnorm(h, L["ln1"], c.eps, out=xn)
+            ops.gemm(xn, L["qkv"], out=qkv)
+            ops.rope_kv_append(qkv, q, self.k_pages[li], self.v_pages[li], seq, pos, slot, self.page_table, self.cos,
+                               self.sin, c.heads, c.head_dim)
+            ops.fmha(q, self.k_pages[li], self.v_pages[li], attn, 1, c.heads, T, Lk, c.head_dim,
+                     (0, c.hidden, c.head_dim), (0, 0, 0), (0, 0, 0), (0, c.hidden, c.head_dim), scale, causal=True,
+                     page_table=pt_row)
+            ops.gemm(attn, L["o"], residual=h, out=h)
+            ops.rmsnorm(h, L["ln2"], c.eps, out=xn)
+            ops.gemm(xn, L["gate_up"], glu=ops.GLU_SWIGLU, out=act)
+            ops.gemm(act, L["down"], residual=h, out=h)
+        hn = ops.rmsnorm(h, w["norm"], c.eps)
+        self.seq_len_h[b] = Lk
+        logits = None
+        if want_logits:
+            logits = ops.skinny_gemm(hn[T - 1:T], w["lm_head"])
+        return hn, logits
+
+    # ------------------------------------------------------------------ decode step (graph body)
+    def _decode_body(self, B):
+        c, w = self.cfg, self.w
+        scale = 1.0 / math.sqrt(c.head_dim)
+        h, xn, qkv, q, attn, act = (t[:B] for t in (self.d_h, self.d_xn, self.d_qkv, self.d_q, self.d_attn, self.d_act))
+        ops.gather_rows(w["embed"], self.cur_ids[:B], h)
+        for li, L in enumerate(w["layers"]):
+            ops.rmsnorm(h, L["ln1"], c.eps, out=xn)
+            ops.skinny_gemm(xn, L["qkv"], out=qkv)
+            ops.rope_kv_append(qkv, q, self.k_pages[li], self.v_pages[li], self.tok_seq[:B], self.tok_pos[:B],
+                               self.tok_slot[:B], self.page_table, self.cos, self.sin, c.heads, c.head_dim)
+            ops.attn_decode_paged(q, self.k_pages[li], self.v_pages[li], self.seq_lens[:B], self.page_table, attn,
+                                  self.d_ws, c.heads, c.head_dim, self.splits, scale)
+            ops.skinny_gemm(attn, L["o"], ops.EPI_RESIDUAL, residual=h, out=h)
+            ops.rmsnorm(h, L["ln2"], c.eps, out=xn)
+            ops.skinny_gemm(xn, L["gate_up"], ops.EPI_SWIGLU, out=act)
+            ops.skinny_gemm(act, L["down"], ops.EPI_RESIDUAL, residual=h, out=h)
+        ops.rmsnorm(h, w["norm"], c.eps, out=xn)
+        ops.store_rows_indexed(xn, self.hist[:B], self.n_out[:B])
+        ops.skinny_gemm(xn, w["lm_head"], out=self.d_logits[:B])
+        ops.logits_process_argmax(self.d_logits[:B], self.cur_ids[:B], self.img_ids, self.next_ids[:B])
+        ops.decode_advance(self.next_ids[:B], self.cur_ids[:B], self.tok_pos[:B], self.tok_slot[:B], self.seq_lens[:B],
+                           self.out_ids[:B], self.n_out[:B], self.done[:B], self.eos_id, self.schedule[:B])
+
+    def decode_step(self, B, use_graph=True):
+        if not use_graph:
+            self._decode_body(B)
+            return
+        g = self._graphs.get(B)
+        if g is None:
+            # warm up outside capture (module-level lazy init: func attributes, tensor-map cache)
+            state = [t.clone() for t in (self.cur_ids, self.tok_pos, self.tok_slot, self.seq_lens, self.n_out,
+                                         self.done, self.out_ids)]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._decode_body(B)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            for t, sv in zip((self.cur_ids, self.tok_pos, self.tok_slot, self.seq_lens, self.n_out, self.done,
+                              self.out_ids), state):
+                t.copy_(sv)
+            g = torch.cuda.CUDAGraph()
+            n0 = _capi.launch_count()
+            with torch.cuda.graph(g):
+                self._decode_body(B)
+            self._graph_launches = _capi.launch_count() - n0
+            for t, sv in zip((self.cur_ids, self.tok_pos, self.tok_slot, self.seq_lens, self.n_out, self.done,
+                              self.out_ids), state):
+                t.copy_(sv)
+            self._graphs[B] = g
+        g.replay()
+        _capi.add_launches(self._graph_launches)
+
+    # ------------------------------------------------------------------ greedy generation (batch of 1..B)
+    def begin_decode(self, first_ids, positions, schedule=None):
+        """Arm the device-side decode state after prefill.  first_ids[b] is the first generated token (already
+        chosen from the prefill logits); positions[b] its RoPE position."""
+        B = len(first_ids)
+        for b in range(B):
+            self._ensure_pages(b, min(self.seq_len_h[b] + self.max_new + 1, self.max_pages * PAGE))
+        i32 = dict(dtype=torch.int32)
+        self.cur_ids[:B].copy_(torch.tensor(first_ids, **i32))
+        self.tok_pos[:B].copy_(torch.tensor(positions, **i32))
+        self.tok_slot[:B].copy_(torch.tensor(self.seq_len_h[:B], **i32))
+        self.seq_lens[:B].copy_(torch.tensor([n + 1 for n in self.seq_len_h[:B]], **i32))
+        self.n_out[:B].fill_(1)
+        self.done[:B].copy_(torch.tensor([1 if t == self.eos_id else 0 for t in first_ids], **i32))
+        self.out_ids[:B, 0].copy_(torch.tensor(first_ids, **i32))
+        if schedule is not None:
+            self.schedule[:B].copy_(schedule)
+        else:
+            self.schedule[:B].fill_(-1)
+
+    def read_step(self, B):
+        """4-byte-per-sequence read-back of the ids just emitted (the only host sync of a decode step)."""
+        self._pinned_ids[:B].copy_(self.cur_ids[:B], non_blocking=True)
+        self._pinned_done[:B].copy_(self.done[:B], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pinned_ids[:B].tolist(), self._pinned_done[:B].tolist()
+
+    def first_token(self, logits, last_id, sched0=-1):
+        """Processor + argmax on prefill logits (same kernel as the decode step)."""
+        last = torch.tensor([last_id], dtype=torch.int32, device=self.dev)
+        nxt = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        ops.logits_process_argmax(logits, last, self.img_ids, nxt)
+        t = int(nxt.item())
+        return sched0 if sched0 >= 0 else t
+
+    def generate(self, b, input_ids, inputs_embeds, max_new_tokens, schedule=None, chunk_image_run=True,
+                 use_graph=True):
+        """Greedy generation for sequence slot b (reference semantics: HF greedy_search with the image-token
+        processor, stop on EOS or max_new_tokens).  `schedule`: optional list (len <= max_new) of forced ids
+        (-1 = free).  Returns (generated ids list, hidden rows [T-1, hidden] where row i is the post-norm hidden
+        state of the position whose input is generated id i)."""
+        assert self.max_batch >= 1 and b == 0, "single-story generate uses slot 0; batched decode goes through begin_decode/decode_step"
+        c = self.cfg
+        L = len(input_ids)
+        self.reset_sequence(b)
+        hn, logits = self.forward_chunk(b, inputs_embeds, list(range(L)))
+        sched = [-1] * self.max_new
+        if schedule is not None:
+            sched[:len(schedule)] = schedule
+        first = self.first_token(logits, int(input_ids[-1]), sched[0])
+        gen = [first]
+        hid_rows = []
+        sched_t = torch.tensor([sched], dtype=torch.int32)
+        boi, eoi = self.img_ids_h[0], self.img_ids_h[-1]
+        n_img = len(self.img_ids_h) - 2
+        armed = False
+        while gen[-1] != self.eos_id and len(gen) < max_new_tokens:
+            if chunk_image_run and gen[-1] == boi and len(gen) + n_img + 1 < max_new_tokens \
+                    and all(s < 0 for s in sched[len(gen):len(gen) + n_img + 1]):
+                # the next n_img+1 ids are input-determined (generation.py:23-26): feed [BOI, IMG_0.., EOI] as ONE chunk
+                run = [boi] + self.img_ids_h[1:-1] + [eoi]
+                emb = self.embed_tokens(torch.tensor(run))
+                p0 = L + len(gen) - 1
+                hn_c, logits = self.forward_chunk(b, emb, list(range(p0, p0 + len(run))))
+                hid_rows.append(hn_c)
+                gen.extend(run[1:])
+                nxt = self.first_token(logits, eoi, sched[len(gen)] if len(gen) < len(sched) else -1)
+                gen.append(nxt)
+                armed = False
+                continue
+            if not armed:
+                self.begin_decode([gen[-1]], [L + len(gen) - 1], sched_t)
+                self.n_out[:1].fill_(len(gen))
+                armed = True
+                step0 = len(gen)
+            self.decode_step(1, use_graph)
+            ids, _ = self.read_step(1)
+            self.seq_len_h[b] += 1
+            hid_rows.append(self.hist[0, len(gen):len(gen) + 1].clone())
+            gen.append(ids[0])
+        hidden = torch.cat(hid_rows, 0) if hid_rows else torch.empty((0, c.hidden), dtype=torch.float16, device=self.dev)
+        return gen, hidden
+
+
+class PagedKVView:
+    """Lazy stand-in for the reference's tuple-of-(K, V) `past_key_values` (models.py:156, 220): indexing layer l
+    gathers that layer's K/V of sequence b out of the page pool as [1, heads, n, head_dim] tensors."""
+
+    def __init__(self, engine, b):
+        self.e, self.b = engine, b
+        self.n = engine.seq_len_h[b]
+        self.pages = engine.page_table_h[b, :(self.n + PAGE - 1) // PAGE].clone().long()
+
+    def __len__(self):
+        return self.e.cfg.layers
+
+    def __getitem__(self, l):
+        e = self.e
+        pg = self.pages.to(e.dev)
+
+        def g(pool):
+            t = pool[l][pg]  # [np, H, 64, D]
+            return t.permute(1, 0, 2, 3).reshape(e.cfg.heads, -1, e.cfg.head_dim)[:, :self.n].unsqueeze(0)
+        return (g(e.k_pages), g(e.v_pages))
+
+    def __iter__(self):
+        for l in range(len(self)):
+            yield self[l]

@@ -11,6 +11,22 @@ from . import _capi
 
 F16, BF16 = 0, 1
 KV_PAGE = 64
+PROFILE = None  # bench.py sets this to a list: (name, algorithmic_flops, start_event, end_event) per tcgen05 launch
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(e0, name, flops):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((name, flops, e0, e1))
 
 
 def _dt(t):
@@ -120,10 +136,25 @@ def gather_rows(table, ids, out):
                _stream())
 
 
-def decode_advance(next_ids, cur_ids, tok_pos, tok_slot, seq_lens, out_ids, n_out, done, eos_id):
+def decode_advance(next_ids, cur_ids, tok_pos, tok_slot, seq_lens, out_ids, n_out, done, eos_id, schedule=None):
     B = next_ids.numel()
     _capi.call("ss_decode_advance", _p(next_ids), _p(cur_ids), _p(tok_pos), _p(tok_slot), _p(seq_lens), _p(out_ids),
-               out_ids.shape[1], _p(n_out), _p(done), eos_id, B, _stream())
+               out_ids.shape[1], _p(n_out), _p(done), eos_id, B, _p(schedule),
+               schedule.shape[1] if schedule is not None else 0, _stream())
+
+
+def store_rows_indexed(src, dst, idx):
+    """dst [B, cap, W]; dst[b, idx[b]] = src[b]."""
+    B, cap, W = dst.shape
+    _capi.call("ss_store_rows_indexed_16b", _p(src), src.stride(0), _p(dst), cap, _p(idx), B, W, _stream())
+
+
+def lora_merge(W, A, B, scaling):
+    out = torch.empty_like(W)
+    N, K = W.shape
+    _capi.call("ss_lora_merge_f16", _p(W), _p(A.contiguous()), _p(B.contiguous()), _p(out), N, K, A.shape[0],
+               ctypes.c_float(scaling), _stream())
+    return out
 
 
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
@@ -142,9 +173,17 @@ def gemm(a, w, bias=None, bias2=None, rows_per_group=0, residual=None, act=ACT_N
     if out is None:
         out = torch.empty((M, n_out), dtype=a.dtype, device=a.device)
     assert out.stride(1) == 1
+    _e = _prof_begin()
     _capi.call("ss_gemm_tn", _dt(a), _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
                _p(bias), _p(bias2), rows_per_group, _p(residual), residual.stride(0) if residual is not None else 0,
                act, glu, ctypes.c_float(alpha), force_bn, _stream())
+    _prof_end(_e, "gemm", 2.0 * M * N * K)
+    return out
+
+
+def unary(x, op, out=None):
+    out = torch.empty_like(x) if out is None else out
+    _capi.call("ss_unary", _dt(x), _p(x), _p(out), ctypes.c_longlong(x.numel()), op, _stream())
     return out
 
 
@@ -156,8 +195,10 @@ def conv3x3(x, w, bias=None, bias2=None, residual=None, act=ACT_NONE, out=None, 
     assert x.is_contiguous() and w.is_contiguous() and w.shape[1] == 9 * Cin
     if out is None:
         out = torch.empty((Nimg, H, W_, Cout), dtype=x.dtype, device=x.device)
+    _e = _prof_begin()
     _capi.call("ss_conv3x3_nhwc", _dt(x), _p(x), _p(w), _p(out), Nimg, H, W_, Cin, Cout, _p(bias), _p(bias2),
-               _p(residual), act, force_bn, _stream())
+               bias2.stride(0) if bias2 is not None else 0, _p(residual), act, force_bn, _stream())
+    _prof_end(_e, "conv3x3", 2.0 * Nimg * H * W_ * Cout * 9 * Cin)
     return out
 
 

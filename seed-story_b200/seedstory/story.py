@@ -1,0 +1,168 @@
+"""End-to-end interleaved story generation through the reference-facing API (the `src.*` drop-in modules).
+
+Mirrors the call sequence of the reference's scripts —
+  src/inference/gen_george.py:152-270 (turn loop, window of 8 images :235-239) with the append-ids prompt
+  bookkeeping of src/inference/vis_george_sink.py:247-263 —
+but as a function, with synthetic StoryStream-shaped inputs: no checkpoints, tokenizer files or
+datasets exist offline, so weights are seeded random tensors of the real shapes and the turn structure
+(64 text tokens -> <img> -> 64 image queries -> </img> -> EOS) is forced through the `logits_processor=` hook
+that ContinuousLVLM.generate exposes.  Text tokens are still the model's true greedy choices.
+"""
+import time
+
+import torch
+
+BOI_TOKEN = '<img>'
+EOI_TOKEN = '</img>'
+IMG_TOKEN = '<img_{:05d}>'
+
+
+class SyntheticTokenizer:
+    """Stand-in for pretrained/cvlm_llama2_tokenizer (32000 Llama ids + <img>, </img>, <img_00000..63>).
+    Id assignment follows SURVEY.md §7: BOI=32000, EOI=32001, IMG_i=32002+i."""
+    bos_token_id, eos_token_id, pad_token_id = 1, 2, 0
+
+    def __init__(self, vocab=32066, n_img=64):
+        self.vocab, self.n_img = vocab, n_img
+        self.boi, self.eoi, self.img0 = vocab - n_img - 2, vocab - n_img - 1, vocab - n_img
+        self._special = {BOI_TOKEN: self.boi, EOI_TOKEN: self.eoi}
+        for i in range(n_img):
+            self._special[IMG_TOKEN.format(i)] = self.img0 + i
+        self._inv = {v: k for k, v in self._special.items()}
+
+    def encode(self, text, add_special_tokens=False):
+        import re
+        ids = []
+        for piece in re.split(r"(<img_\d{5}>|</img>|<img>)", text):
+            if not piece:
+                continue
+            if piece in self._special:
+                ids.append(self._special[piece])
+            else:  # "words" are space-separated decimal ids, e.g. "t17 t905"
+                ids.extend(int(w[1:]) for w in piece.split() if w.startswith("t"))
+        return ids
+
+    def decode(self, ids, skip_special_tokens=False):
+        ids = ids.tolist() if hasattr(ids, "tolist") else list(ids)
+        return " ".join(self._inv.get(i, f"t{i}") for i in ids)
+
+
+FULL = dict(
+    llama=dict(hidden_size=4096, intermediate_size=11008, num_attention_heads=32, num_hidden_layers=32,
+               vocab_size=32000, rms_norm_eps=1e-5),
+    vocab=32066,
+    vit=dict(heads=16, image_size=448, layers=48, mlp_ratio=4.9231, output_dim=4096, patch_size=14, width=1664),
+    agent_dim=4096, agent_heads=32,
+    xl=dict(dim=1024, depth=4, dim_head=64, heads=16, num_queries=64, embedding_dim=4096, output1_dim=768,
+            output2_dim=1280, ff_mult=4),
+    unet=None, vae=None, image=1024,
+)
+
+# reduced-size configuration for tests (same structure, every kernel path exercised)
+TINY = dict(
+    llama=dict(hidden_size=256, intermediate_size=352, num_attention_heads=2, num_hidden_layers=2,
+               vocab_size=254, rms_norm_eps=1e-5),
+    vocab=320,
+    vit=dict(heads=4, image_size=56, layers=2, mlp_ratio=4.0, output_dim=256, patch_size=14, width=64,
+             n_queries=256),
+    agent_dim=256, agent_heads=2,
+    xl=dict(dim=256, depth=2, dim_head=64, heads=4, num_queries=64, embedding_dim=256, output1_dim=96,
+            output2_dim=160, ff_mult=4),
+    unet=dict(block_out_channels=(64, 128, 256), num_attention_heads=(1, 2, 4), transformer_layers_per_block=(0, 1, 2),
+              cross_attention_dim=256, projection_class_embeddings_input_dim=160 + 6 * 32, addition_time_embed_dim=32,
+              sample_size=32),
+    vae=dict(block_out_channels=(64, 64, 128, 128)), image=256,
+)
+
+
+class StoryPipeline:
+    def __init__(self, device="cuda:0", cfg=None, seed=1234, num_inference_steps=50, n_text_tokens=64,
+                 window_size=8, verbose=False):
+        import diffusers
+        from src.models.discrete_models import DiscreteModleIdentity
+        from src.models.qwen_visual import Resampler, VisionTransformerWithAttnPool
+        from src.models_clm.modeling_llama_xformer import LlamaForCausalLM
+        from src.models_clm.models import ContinuousLVLM
+        from src.models_clm.peft_models import LoraConfig, get_peft_model_with_resize_embedding
+        from src.models_ipa.adapter_modules import SDXLAdapter
+        from src.models_ipa.resampler import ResamplerXLV2
+        cfg = cfg or FULL
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.steps, self.n_text, self.window = num_inference_steps, n_text_tokens, window_size
+        torch.manual_seed(seed)
+        dt = torch.float16
+        t0 = time.time()
+        with torch.device(self.dev):
+            self.tokenizer = SyntheticTokenizer(cfg["vocab"], 64)
+            self.visual_encoder = VisionTransformerWithAttnPool(**cfg["vit"]).eval().to(dtype=dt)
+            llama = LlamaForCausalLM(cfg["llama"]).to(dtype=dt)
+            peft_cfg = LoraConfig(r=16, lora_alpha=32, target_modules=["q_proj", "v_proj", "k_proj", "o_proj",
+                                                                       "gate_proj", "down_proj", "up_proj"],
+                                  modules_to_save=["input_layernorm", "post_attention_layernorm", "norm"],
+                                  lora_dropout=0.05, task_type="CAUSAL_LM")
+            llm = get_peft_model_with_resize_embedding(llama, peft_config=peft_cfg, vocab_size=cfg["vocab"],
+                                                       torch_dtype="fp16")
+            # peft initialises lora_B to zero; give it N(0, 0.02^2) so the LoRA path carries signal
+            for n, p in llm.named_parameters():
+                if "lora_B" in n:
+                    torch.nn.init.normal_(p, std=0.02)
+            E, Hh = cfg["agent_dim"], cfg["agent_heads"]
+            self.agent = ContinuousLVLM(llm, Resampler(8, E, Hh, kv_dim=E), Resampler(16, E, Hh, kv_dim=E)).eval().to(dtype=dt)
+            self.scheduler = diffusers.EulerDiscreteScheduler()
+            self.vae = diffusers.AutoencoderKL(config=cfg["vae"]).to(dtype=dt)
+            self.unet = diffusers.UNet2DConditionModel(config=cfg["unet"]).to(dtype=dt)
+            self.adapter = SDXLAdapter(self.unet, ResamplerXLV2(**cfg["xl"])).to(dtype=dt).eval()
+            self.discrete = DiscreteModleIdentity().eval()
+        self.adapter.init_pipe(vae=self.vae, scheduler=self.scheduler, visual_encoder=self.visual_encoder,
+                               image_transform=None, discrete_model=self.discrete, dtype=dt, device=self.dev)
+        tk = self.tokenizer
+        self.image_ids = [tk.boi] + [tk.img0 + i for i in range(64)] + [tk.eoi]
+        if verbose:
+            print(f"[story] models built in {time.time() - t0:.1f}s")
+
+    def _schedule(self):
+        """text tokens free (greedy), then <img> forced; the 64 queries + </img> come from the image-token processor;
+        EOS forced afterwards."""
+        from src.models_clm.generation import ForcedScheduleProcessor
+        tk = self.tokenizer
+        sched = [-1] * self.n_text + [tk.boi] + [-1] * 65 + [tk.eos_token_id]
+        return ForcedScheduleProcessor(sched)
+
+    @torch.no_grad()
+    def run_story(self, image_tensor, caption_ids, n_turns, decode_images=True, return_images=False):
+        """image_tensor [1,3,S,S] fp16 on the device (CLIP-normalised); caption_ids: list[int].
+        Returns list of per-turn dicts(generate_ids, image_uint8 | None)."""
+        from src.models_clm.generation import AutoImageTokenGenerationProcessor
+        tk, dev = self.tokenizer, self.dev
+        input_ids = [tk.bos_token_id] + list(caption_ids) + self.image_ids
+        image_embeds = self.visual_encoder(image_tensor)
+        procs = [AutoImageTokenGenerationProcessor(tk, 64), self._schedule()]
+        outs = []
+        res = self.cfg["image"]
+        for turn in range(n_turns):
+            ids_t = torch.tensor([input_ids], dtype=torch.long, device=dev)
+            boi = [i for i, t in enumerate(input_ids) if t == tk.boi]
+            eoi = [i for i, t in enumerate(input_ids) if t == tk.eoi]
+            ids_cmp_mask = torch.zeros_like(ids_t, dtype=torch.bool)
+            for i in range(image_embeds.shape[0]):
+                ids_cmp_mask[0, boi[i] + 1:eoi[i]] = True
+            embeds_cmp_mask = torch.ones(image_embeds.shape[0], dtype=torch.bool, device=dev)
+            out = self.agent.generate(tokenizer=tk, input_ids=ids_t, image_embeds=image_embeds,
+                                      embeds_cmp_mask=embeds_cmp_mask, ids_cmp_mask=ids_cmp_mask,
+                                      max_new_tokens=500, num_img_gen_tokens=64, logits_processor=procs, device=dev)
+            assert out["has_img_output"], "forced schedule must produce an image run"
+            img = None
+            if decode_images:
+                imgs = self.adapter.generate(image_embeds=out["img_gen_feat"], num_inference_steps=self.steps,
+                                             height=res, width=res, output_type="pt")
+                img = imgs[0]
+            gen = out["generate_ids"].tolist()
+            outs.append(dict(generate_ids=gen, image=img if return_images else None))
+            image_embeds = torch.cat((image_embeds, out["img_gen_feat"]), dim=0)
+            text_ids = [t for t in gen if t < tk.boi and t != tk.eos_token_id]
+            input_ids = input_ids + text_ids + self.image_ids
+            while image_embeds.shape[0] > self.window:  # evict the oldest image and all text before it
+                first_eoi = input_ids.index(tk.eoi)
+                input_ids = [tk.bos_token_id] + input_ids[first_eoi + 1:]
+                image_embeds = image_embeds[1:]
+        return outs
