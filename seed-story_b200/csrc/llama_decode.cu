@@ -247,8 +247,11 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
   unpack8<__half>(*reinterpret_cast<const vec8*>(qs + l16 * 8), qf);
   const int* pt = page_table + (size_t)b * max_pages;
   float lmax = -INFINITY;
-  for (int j = warp * 2 + sub; j < cnt; j += (AD_THREADS / 32) * 2) {
-    const int tok = t0 + j;
+  // warp-uniform trip count: the half-warp shuffles below need all 32 lanes converged
+  for (int j0 = warp * 2; j0 < cnt; j0 += (AD_THREADS / 32) * 2) {
+    const int j = j0 + sub;
+    const bool valid = j < cnt;
+    const int tok = t0 + (valid ? j : 0);
     const int page = pt[tok / KV_PAGE];
     const __half* kr = kcache + (((size_t)page * H + h) * KV_PAGE + (tok % KV_PAGE)) * D + l16 * 8;
     float kf[8];
@@ -259,8 +262,10 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
     d *= scale;
-    if (l16 == 0) sc[j] = d;
-    lmax = fmaxf(lmax, d);
+    if (valid) {
+      if (l16 == 0) sc[j] = d;
+      lmax = fmaxf(lmax, d);
+    }
   }
   const float m = block_max(lmax, red);
   // phase 2: exponentials
