@@ -87,6 +87,13 @@ SS_EXPORT int ss_store_rows_indexed_16b(const void* src, int ld_src, void* dst, 
 SS_EXPORT int ss_lora_merge_f16(const void* W, const void* A, const void* B, void* out, int N, int K, int r,
                                 float scaling, void* stream);
 
+/* KV compaction for the image window / multimodal attention sink: destination slot i <- source slot src_idx[i]
+ * in every layer (replaces the torch.cat slicing of src/inference/vis_george_sink.py:266-291 and the window cut of
+ * src/inference/gen_george.py:235-239).  Source and destination page lists must be disjoint. */
+SS_EXPORT int ss_kv_gather_tokens_16b(void* kpool, void* vpool, int layers, long long layer_stride,
+                                      const int* src_pages, const int* dst_pages, const int* src_idx, int n, int H,
+                                      int D, void* stream);
+
 /* ---- dense contractions on tcgen05 ------------------------------------------------------------ */
 /* C[M,N] = epi(alpha * A[M,K] B[N,K]^T): every nn.Linear on the prefill / ViT / resampler / UNet /
  * VAE paths (e.g. qwen_visual.py:191,233,258-260; resampler.py:58-76; modeling_llama_xformer.py:228-230).

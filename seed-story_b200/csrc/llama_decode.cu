@@ -519,3 +519,36 @@ SS_API int ss_lora_merge_f16(const void* W, const void* A, const void* B, void* 
   SS_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// KV compaction for the window / multimodal attention-sink policy (src/inference/vis_george_sink.py:266-291):
+// token slot i of the destination page list receives the K and V rows of source slot src_idx[i], for every
+// layer.  Afterwards the sequence is again a dense [sink tokens..., live tokens...] run of pages, so the
+// attention kernels need no per-token mask.  Pools: [layer][page][H][64][D].
+// ---------------------------------------------------------------------------------------------
+__global__ void kv_gather_tokens_kernel(uint16_t* __restrict__ kpool, uint16_t* __restrict__ vpool,
+                                        long long layer_stride, const int* __restrict__ src_pages,
+                                        const int* __restrict__ dst_pages, const int* __restrict__ src_idx, int H,
+                                        int D) {
+  const int i = blockIdx.x, layer = blockIdx.y;
+  const int s = src_idx[i];
+  const size_t src = (size_t)layer * layer_stride + ((size_t)src_pages[s / KV_PAGE] * H * KV_PAGE + (s % KV_PAGE)) * D;
+  const size_t dst = (size_t)layer * layer_stride + ((size_t)dst_pages[i / KV_PAGE] * H * KV_PAGE + (i % KV_PAGE)) * D;
+  const int vec_per_row = D >> 3;
+  for (int t = threadIdx.x; t < H * vec_per_row; t += blockDim.x) {
+    const int h = t / vec_per_row, v = t % vec_per_row;
+    const size_t off = (size_t)h * KV_PAGE * D + v * 8;
+    *reinterpret_cast<vec8*>(kpool + dst + off) = *reinterpret_cast<const vec8*>(kpool + src + off);
+    *reinterpret_cast<vec8*>(vpool + dst + off) = *reinterpret_cast<const vec8*>(vpool + src + off);
+  }
+}
+SS_API int ss_kv_gather_tokens_16b(void* kpool, void* vpool, int layers, long long layer_stride, const int* src_pages,
+                                   const int* dst_pages, const int* src_idx, int n, int H, int D, void* stream) {
+  SS_REQUIRE(D % 8 == 0, "head_dim % 8");
+  if (n == 0) return 0;
+  kv_gather_tokens_kernel<<<dim3(n, layers), 256, 0, (cudaStream_t)stream>>>((uint16_t*)kpool, (uint16_t*)vpool,
+                                                                              layer_stride, src_pages, dst_pages,
+                                                                              src_idx, H, D);
+  SS_LAUNCH_CHECK();
+  return 0;
+}

@@ -150,6 +150,29 @@ class LlamaEngine:
         if changed:
             self.page_table[b].copy_(self.page_table_h[b], non_blocking=True)
 
+    def retain_tokens(self, b, keep):
+        """Keep only cache slots `keep` (sorted list of slot indices) of sequence b, compacted into fresh pages:
+        the window cut (gen_george.py:235-239) and the attention-sink retention (vis_george_sink.py:266-291).
+        Keys keep their original RoPE phase (they are cached post-RoPE, modeling_llama_xformer.py:236-244)."""
+        keep = list(keep)
+        n = len(keep)
+        assert all(0 <= k < self.seq_len_h[b] for k in keep) and keep == sorted(set(keep))
+        old_n = self.n_pages_owned[b]
+        old_pages = self.page_table_h[b, :old_n].clone()
+        need = (n + PAGE - 1) // PAGE
+        new_pages = torch.tensor([self.free_pages.pop() for _ in range(need)], dtype=torch.int32)
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        if n:
+            ops.kv_gather_tokens(self.k_pages, self.v_pages, old_pages.to(self.dev), new_pages.to(self.dev),
+                                 torch.tensor(keep, **i32), self.cfg.heads, self.cfg.head_dim)
+        torch.cuda.current_stream().synchronize()  # old pages are recycled below
+        self.free_pages.extend(old_pages.tolist())
+        self.page_table_h[b].zero_()
+        self.page_table_h[b, :need] = new_pages
+        self.page_table[b].copy_(self.page_table_h[b])
+        self.n_pages_owned[b] = need
+        self.seq_len_h[b] = n
+
     # ------------------------------------------------------------------ prefill / chunk
     def forward_chunk(self, b, embeds, positions, want_logits=True):
         """Run T tokens of sequence b on top of its cache (prefill when the cache is empty).
@@ -353,3 +376,15 @@ class PagedKVView:
     def __iter__(self):
         for l in range(len(self)):
             yield self[l]
+
+
+def sink_retained_slots(seq_len, evicted_images, live_from, n_sink=4, head=(4, 8), tail=(8, 4)):
+    """Retention set of the multimodal attention sink (vis_george_sink.py:266-291, SURVEY.md §7 "Sink semantics"):
+    slots {0..n_sink-1} U for every evicted image (boi, eoi): [boi-4, boi+8) U [eoi-8, eoi+4) U the live tail
+    [live_from, seq_len).  Returns a sorted list of slot indices."""
+    keep = set(range(min(n_sink, seq_len)))
+    for boi, eoi in evicted_images:
+        keep.update(range(max(0, boi - head[0]), min(seq_len, boi + head[1])))
+        keep.update(range(max(0, eoi - tail[0]), min(seq_len, eoi + tail[1])))
+    keep.update(range(live_from, seq_len))
+    return sorted(keep)

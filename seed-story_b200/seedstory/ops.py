@@ -149,6 +149,13 @@ def store_rows_indexed(src, dst, idx):
     _capi.call("ss_store_rows_indexed_16b", _p(src), src.stride(0), _p(dst), cap, _p(idx), B, W, _stream())
 
 
+def kv_gather_tokens(k_pages, v_pages, src_pages, dst_pages, src_idx, H, D):
+    """k_pages/v_pages [layers, pages, H, 64, D]; page lists and src_idx are int32 device tensors."""
+    layers = k_pages.shape[0]
+    _capi.call("ss_kv_gather_tokens_16b", _p(k_pages), _p(v_pages), layers, ctypes.c_longlong(k_pages.stride(0)),
+               _p(src_pages), _p(dst_pages), _p(src_idx), src_idx.numel(), H, D, _stream())
+
+
 def lora_merge(W, A, B, scaling):
     out = torch.empty_like(W)
     N, K = W.shape

@@ -114,3 +114,32 @@ def test_llama_decode_steps_match_oracle(cuda_dev):
             feats = LO.lvlm_postprocess(gen_ref, hid[L:], 301, 8)
             e = [i for i, t in enumerate(gen) if t == 301][-1]
             assert _rel(hidden_rows[e - 8:e], feats) < 2e-2
+
+
+def test_sink_kv_compaction_matches_oracle_with_sliced_past(cuda_dev):
+    """Attention-sink mode: after retaining {first 4} U {window around an evicted <img>/</img>} U live tail, the next
+    chunk must equal the oracle fed with the correspondingly sliced past_key_values (keys keep their RoPE phase)."""
+    from oracle import llama_oracle as LO
+    from seedstory import llama_engine
+    hidden, inter, heads, layers, vocab = 256, 352, 2, 3, 320
+    p = LO.LlamaParams.random(hidden, inter, heads, layers, vocab, lora_r=0, seed=9, std=0.05)
+    eng = _engine_from_params(p, cuda_dev)
+    g = torch.Generator().manual_seed(4)
+    T = 150
+    emb = torch.randn(1, T, hidden, generator=g) * 0.5
+    eng.forward_chunk(0, emb[0].to(cuda_dev, torch.float16), list(range(T)))
+    _, _, kv = LO.model_forward(p, emb, torch.arange(T).unsqueeze(0), None, max_pos=512)
+    keep = llama_engine.sink_retained_slots(T, evicted_images=[(20, 85)], live_from=86)
+    assert keep[:4] == [0, 1, 2, 3] and 16 in keep and 27 in keep and 28 not in keep and 77 in keep and 76 not in keep
+    before = llama_engine.PagedKVView(eng, 0)[1][0].clone()
+    eng.retain_tokens(0, keep)
+    after = llama_engine.PagedKVView(eng, 0)[1][0]
+    assert torch.equal(after, before[:, :, keep]), "compaction must move K rows bit-exactly"
+    # continue with a 7-token chunk at window-relative positions (prepare_inputs_for_generation :804-826)
+    T1 = 7
+    emb1 = torch.randn(1, T1, hidden, generator=g) * 0.5
+    pos1 = list(range(len(keep), len(keep) + T1))
+    hn, lg = eng.forward_chunk(0, emb1[0].to(cuda_dev, torch.float16), pos1)
+    kv_s = [(k[:, :, keep], v[:, :, keep]) for (k, v) in kv]
+    lo, hn_ref, _ = LO.model_forward(p, emb1, torch.tensor([pos1]), kv_s, max_pos=512)
+    assert _rel(lg[0], lo[0, -1]) < 1e-2 and _rel(hn, hn_ref[0]) < 1e-2
