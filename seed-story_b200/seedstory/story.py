@@ -70,8 +70,8 @@ TINY = dict(
             output2_dim=160, ff_mult=4),
     unet=dict(block_out_channels=(64, 128, 256), num_attention_heads=(1, 2, 4), transformer_layers_per_block=(0, 1, 2),
               cross_attention_dim=256, projection_class_embeddings_input_dim=160 + 6 * 32, addition_time_embed_dim=32,
-              sample_size=32),
-    vae=dict(block_out_channels=(64, 64, 128, 128)), image=256,
+              sample_size=64),
+    vae=dict(block_out_channels=(64, 64, 128, 128)), image=512,
 )
 
 
@@ -154,7 +154,8 @@ class StoryPipeline:
             img = None
             if decode_images:
                 imgs = self.adapter.generate(image_embeds=out["img_gen_feat"], num_inference_steps=self.steps,
-                                             height=res, width=res, output_type="pt")
+                                             height=res, width=res, output_type="pt",
+                                             input_image_size=self.cfg["vit"]["image_size"])
                 img = imgs[0]
             gen = out["generate_ids"].tolist()
             outs.append(dict(generate_ids=gen, image=img if return_images else None))

@@ -139,7 +139,7 @@ def test_logits_processor_argmax(cuda_dev):
     B = 4
     logits = torch.randn(B, V, device=cuda_dev).half()
     logits[0, 32010] = 50.0          # would win, but gets zeroed (not in an image run)
-    logits[0, :32000] -= 10.0        # everything else negative -> zeroed ids win at 0.0, lowest index first
+    logits[0, :32001] -= 10.0        # everything else (incl. the untouched BOI) negative -> zeroed ids win at 0.0, lowest index first
     last = torch.tensor([17, 32000, 32002 + 63, 32001], device=cuda_dev, dtype=torch.int32)
     ref_logits = logits.clone()
     nxt = torch.empty(B, device=cuda_dev, dtype=torch.int32)

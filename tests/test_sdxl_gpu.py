@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 TINY_UNET = dict(in_channels=4, out_channels=4, block_out_channels=(64, 128, 256), layers_per_block=2,
                  transformer_layers_per_block=(0, 1, 2), num_attention_heads=(1, 2, 4), cross_attention_dim=256,
                  addition_time_embed_dim=32, projection_class_embeddings_input_dim=160 + 6 * 32, norm_num_groups=32,
-                 sample_size=32)
+                 sample_size=64)
 TINY_VAE = dict(latent_channels=4, out_channels=3, block_out_channels=(64, 64, 128, 128), layers_per_block=2,
                 norm_num_groups=32, scaling_factor=0.13025)
 
@@ -90,7 +90,7 @@ def test_story_pipeline_tiny_end_to_end(cuda_dev):
     for o in outs:
         g = o["generate_ids"]
         assert g[5] == tk.boi and g[6:70] == [tk.img0 + i for i in range(64)] and g[70] == tk.eoi and g[71] == tk.eos_token_id
-        assert o["image"].shape == (256, 256, 3) and o["image"].dtype == torch.uint8
+        assert o["image"].shape == (512, 512, 3) and o["image"].dtype == torch.uint8
     # determinism: same inputs -> identical tokens and pixels
     outs2 = pipe.run_story(img, cap, n_turns=3, return_images=True)
     assert [o["generate_ids"] for o in outs] == [o["generate_ids"] for o in outs2]
