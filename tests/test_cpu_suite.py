@@ -228,3 +228,27 @@ def test_world_size_2_sharding_gloo():
     assert all(r[1] == 11.0 for r in res)                       # max over ranks
     d = res[0][2]
     assert d[0] != d[1], "ranks must work on different stories (seed 1000+s with s offset by rank)"
+
+
+def test_hydra_shim_instantiates_reference_style_configs(tmp_path):
+    """One YAML = one object with `_target_` paths identical to the reference's configs."""
+    import hydra
+    from omegaconf import OmegaConf
+    (tmp_path / "agent.yaml").write_text(
+        "_target_: src.models_clm.models.ContinuousLVLM.from_pretrained\n"
+        "input_resampler:\n  _target_: src.models.qwen_visual.Resampler\n  grid_size: 8\n  embed_dim: 256\n  num_heads: 2\n  kv_dim: 256\n"
+        "output_resampler:\n  _target_: src.models.qwen_visual.Resampler\n  grid_size: 16\n  embed_dim: 256\n  num_heads: 2\n  kv_dim: 256\n"
+        "lm_loss_scale: 1.0\nrec_loss_scale: 1.0\npretrained_model_path: pretrained/does_not_exist.bin\n")
+    (tmp_path / "tf.yaml").write_text("_target_: src.processer.transforms.get_transform\ntype: clip\nimage_size: 448\nkeep_ratio: False\n")
+    (tmp_path / "id.yaml").write_text("_target_: src.models.discrete_models.DiscreteModleIdentity\n")
+    (tmp_path / "lora.yaml").write_text(
+        "_target_: peft.LoraConfig\n_convert_: object\nr: 16\nlora_alpha: 32\nmodules_to_save:\n  - norm\n"
+        "target_modules:\n  - q_proj\n  - v_proj\ntask_type: CAUSAL_LM\nlora_dropout: 0.05\n")
+    agent = hydra.utils.instantiate(OmegaConf.load(tmp_path / "agent.yaml"), llm=torch.nn.Identity())
+    assert type(agent).__name__ == "ContinuousLVLM" and agent.input_resampler.num_queries == 64
+    tf = hydra.utils.instantiate(OmegaConf.load(tmp_path / "tf.yaml"))
+    from PIL import Image
+    assert tf(Image.new("RGB", (300, 200))).shape == (3, 448, 448)
+    assert hydra.utils.instantiate(OmegaConf.load(tmp_path / "id.yaml")).encode_image_embeds(3) == 3
+    lc = hydra.utils.instantiate(OmegaConf.load(tmp_path / "lora.yaml"))
+    assert lc.r == 16 and lc.target_modules == ["q_proj", "v_proj"]
