@@ -109,9 +109,9 @@ class StoryPipeline:
             E, Hh = cfg["agent_dim"], cfg["agent_heads"]
             self.agent = ContinuousLVLM(llm, Resampler(8, E, Hh, kv_dim=E), Resampler(16, E, Hh, kv_dim=E)).eval().to(dtype=dt)
             self.scheduler = diffusers.EulerDiscreteScheduler()
-            self.vae = diffusers.AutoencoderKL(config=cfg["vae"]).to(dtype=dt)
-            self.unet = diffusers.UNet2DConditionModel(config=cfg["unet"]).to(dtype=dt)
-            self.adapter = SDXLAdapter(self.unet, ResamplerXLV2(**cfg["xl"])).to(dtype=dt).eval()
+            self.vae = diffusers.AutoencoderKL(config=cfg["vae"]).to(self.dev, dtype=dt)
+            self.unet = diffusers.UNet2DConditionModel(config=cfg["unet"]).to(self.dev, dtype=dt)
+            self.adapter = SDXLAdapter(self.unet, ResamplerXLV2(**cfg["xl"])).to(self.dev, dtype=dt).eval()
             self.discrete = DiscreteModleIdentity().eval()
         self.adapter.init_pipe(vae=self.vae, scheduler=self.scheduler, visual_encoder=self.visual_encoder,
                                image_transform=None, discrete_model=self.discrete, dtype=dt, device=self.dev)
