@@ -90,17 +90,15 @@ SS_API int ss_scatter_rows_16b(const void* src, const int* dst_rows, void* dst, 
 }
 
 // ---- GroupNorm on NHWC (diffusers ResnetBlock2D norm1/norm2, Transformer2D norm, VAE norms) --------
-// pass 1: per-(image, group) sum / sum-of-squares in fp32; pass 2: normalise, affine, optional SiLU.
+// pass 1: per-CTA partial (sum, sum of squares) per (image, group), reduced in a FIXED order (no float atomics:
+// results are bit-reproducible run to run); pass 2: fold the partials into (mean, rstd); pass 3: normalise,
+// affine, optional SiLU.
 template <typename T>
-__global__ void groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int HW, int C, int groups,
-                                       int pix_per_cta) {
-  extern __shared__ float gsm[];  // [2*C]
-  float* csum = gsm;
-  float* csq = gsm + C;
+__global__ void groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW, int C,
+                                         int groups, int pix_per_cta) {
+  extern __shared__ float gsm[];  // [nl][2*C]
   const int n = blockIdx.y;
   const int vecs = C >> 3;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) gsm[i] = 0.f;
-  __syncthreads();
   const int nl = blockDim.x / vecs;  // pixel lanes
   const int v = threadIdx.x % vecs, lane = threadIdx.x / vecs;
   if (lane < nl) {
@@ -118,31 +116,52 @@ __global__ void groupnorm_stats_kernel(const T* __restrict__ x, float* __restric
         q[j] += f[j] * f[j];
       }
     }
+    float* row = gsm + (size_t)lane * 2 * C;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&csum[v * 8 + j], s[j]);
-      atomicAdd(&csq[v * 8 + j], q[j]);
+      row[v * 8 + j] = s[j];
+      row[C + v * 8 + j] = q[j];
     }
   }
   __syncthreads();
   const int cg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float s = 0.f, q = 0.f;
-    for (int c = g * cg; c < (g + 1) * cg; ++c) {
-      s += csum[c];
-      q += csq[c];
+    for (int l = 0; l < nl; ++l) {
+      const float* row = gsm + (size_t)l * 2 * C;
+      for (int c = g * cg; c < (g + 1) * cg; ++c) {
+        s += row[c];
+        q += row[C + c];
+      }
     }
-    atomicAdd(&stats[((size_t)n * groups + g) * 2], s);
-    atomicAdd(&stats[((size_t)n * groups + g) * 2 + 1], q);
+    float* out = partial + (((size_t)n * gridDim.x + blockIdx.x) * groups + g) * 2;
+    out[0] = s;
+    out[1] = q;
   }
+}
+
+__global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int chunks,
+                                          int groups, float inv_cnt, float eps, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g)
+  if (i >= total) return;
+  const int n = i / groups, g = i % groups;
+  float s = 0.f, q = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    const float* p = partial + (((size_t)n * chunks + c) * groups + g) * 2;
+    s += p[0];
+    q += p[1];
+  }
+  const float mean = s * inv_cnt;
+  const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+  stats[2 * i] = mean;
+  stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
 template <typename T>
 __global__ void groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
                                        const T* __restrict__ gamma, const T* __restrict__ beta, int HW, int C,
-                                       int groups, float eps, int silu, long long total_vecs) {
+                                       int groups, int silu, long long total_vecs) {
   const int vecs = C >> 3, cg = C / groups;
-  const float inv_cnt = 1.f / ((float)HW * (float)cg);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vecs;
        i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % vecs);
@@ -155,10 +174,8 @@ __global__ void groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (v * 8 + j) / cg;
-      const float s = stats[((size_t)n * groups + g) * 2], q = stats[((size_t)n * groups + g) * 2 + 1];
-      const float mean = s * inv_cnt;
-      const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
-      float o = (f[j] - mean) * rsqrtf(var + eps) * gm[j] + bt[j];
+      const float mean = stats[((size_t)n * groups + g) * 2], rstd = stats[((size_t)n * groups + g) * 2 + 1];
+      float o = (f[j] - mean) * rstd * gm[j] + bt[j];
       if (silu) {
         o = ss_num<T>::to_f(ss_num<T>::from_f(o));  // GroupNorm output is rounded before the activation module
         o = o / (1.f + __expf(-o));
@@ -169,36 +186,56 @@ __global__ void groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ 
   }
 }
 
+// workspace layout (floats): [2*N*groups stats][N*chunks*groups*2 partials]; ss_groupnorm_ws_floats() sizes it.
+static inline void groupnorm_geometry(int N, int HW, int C, int* block, int* chunks, int* pix_per_cta) {
+  const int vecs = C / 8;
+  *block = vecs <= 256 ? vecs * (256 / vecs) : vecs;
+  int ch = (148 * 4 + N - 1) / N;
+  int ppc = (HW + ch - 1) / ch;
+  if (ppc < 32) ppc = 32;
+  *pix_per_cta = ppc;
+  *chunks = (HW + ppc - 1) / ppc;
+}
+
+SS_API int ss_groupnorm_ws_floats(int N, int HW, int C, int groups) {
+  int block, chunks, ppc;
+  groupnorm_geometry(N, HW, C, &block, &chunks, &ppc);
+  return 2 * N * groups + 2 * N * chunks * groups;
+}
+
 SS_API int ss_groupnorm_nhwc(int dtype, const void* x, void* y, const void* gamma, const void* beta, float* stats_ws,
                              int N, int HW, int C, int groups, float eps, int silu, void* stream) {
   SS_REQUIRE(C % 8 == 0 && C % groups == 0 && C <= 4096, "C % 8, C % groups, C <= 4096");
   SS_REQUIRE(dtype == SS_F16 || dtype == SS_BF16, "dtype");
   if (N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  SS_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * N * groups, s));
-  const int vecs = C / 8;
-  int block = vecs <= 256 ? vecs * (256 / vecs) : vecs;
+  int block, chunks, pix_per_cta;
+  groupnorm_geometry(N, HW, C, &block, &chunks, &pix_per_cta);
   SS_REQUIRE(block <= 1024, "C too large for the GroupNorm stats kernel");
-  int chunks = (148 * 4 + N - 1) / N;
-  int pix_per_cta = (HW + chunks - 1) / chunks;
-  if (pix_per_cta < 32) pix_per_cta = 32;
-  chunks = (HW + pix_per_cta - 1) / pix_per_cta;
+  const int vecs = C / 8, nl = block / vecs;
+  const size_t smem = (size_t)nl * 2 * C * sizeof(float);
+  SS_REQUIRE(smem <= 48 * 1024, "GroupNorm partial kernel shared memory");
+  float* stats = stats_ws;
+  float* partial = stats_ws + 2 * N * groups;
   const long long total_vecs = (long long)N * HW * vecs;
-  if (dtype == SS_F16) {
-    groupnorm_stats_kernel<__half><<<dim3(chunks, N), block, 2 * C * sizeof(float), s>>>((const __half*)x, stats_ws, HW,
-                                                                                        C, groups, pix_per_cta);
-    SS_LAUNCH_CHECK();
+  const float inv_cnt = 1.f / ((float)HW * (float)(C / groups));
+  if (dtype == SS_F16)
+    groupnorm_partial_kernel<__half><<<dim3(chunks, N), block, smem, s>>>((const __half*)x, partial, HW, C, groups,
+                                                                        pix_per_cta);
+  else
+    groupnorm_partial_kernel<__nv_bfloat16><<<dim3(chunks, N), block, smem, s>>>((const __nv_bfloat16*)x, partial, HW,
+                                                                               C, groups, pix_per_cta);
+  SS_LAUNCH_CHECK();
+  groupnorm_finalize_kernel<<<ceil_div(N * groups, 128), 128, 0, s>>>(partial, stats, chunks, groups, inv_cnt, eps,
+                                                                     N * groups);
+  SS_LAUNCH_CHECK();
+  if (dtype == SS_F16)
     groupnorm_apply_kernel<__half><<<ew_grid(total_vecs), EW_THREADS, 0, s>>>(
-        (const __half*)x, (__half*)y, stats_ws, (const __half*)gamma, (const __half*)beta, HW, C, groups, eps, silu,
-        total_vecs);
-  } else {
-    groupnorm_stats_kernel<__nv_bfloat16><<<dim3(chunks, N), block, 2 * C * sizeof(float), s>>>(
-        (const __nv_bfloat16*)x, stats_ws, HW, C, groups, pix_per_cta);
-    SS_LAUNCH_CHECK();
+        (const __half*)x, (__half*)y, stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, silu, total_vecs);
+  else
     groupnorm_apply_kernel<__nv_bfloat16><<<ew_grid(total_vecs), EW_THREADS, 0, s>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, stats_ws, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-        HW, C, groups, eps, silu, total_vecs);
-  }
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, stats, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, HW,
+        C, groups, silu, total_vecs);
   SS_LAUNCH_CHECK();
   return 0;
 }

@@ -7,6 +7,7 @@
 //     is a 4-D TMA box shifted by (ky-1, kx-1); out-of-bounds pixels are zero-filled by the TMA unit,
 //     which IS the conv padding.
 // Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <type_traits>
@@ -239,6 +240,254 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
   if (warp == 1) tc::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
+
+// =============================================================================================
+// v2: persistent kernel.  One CTA per SM loops over output tiles (n fastest, so consecutive CTAs share the
+// A tile through L2); the TMA->smem ring runs continuously across tiles; TMEM holds TWO accumulators so the
+// MMA of tile i+1 overlaps the epilogue of tile i; the epilogue stages fp16/bf16 rows in swizzled shared
+// memory and writes them with TMA tile stores (full 128-byte lines, bounds clipped by the tensor map).
+// =============================================================================================
+template <int BN>
+struct PersistLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
+  static constexpr int STAGING_BYTES = 4 /*warps*/ * 2 /*bufs*/ * 32 * 128;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <typename T, int BN, bool CONV>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmB,
+                                                                         const __grid_constant__ CUtensorMap tmC,
+                                                                         const GemmParams p, int n_tiles_n,
+                                                                         int total_tiles) {
+  using L = PersistLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + L::STAGES * L::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + L::STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + L::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + L::STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kchunks = CONV ? (p.Cin / BK) : ((p.K + BK - 1) / BK);
+  const int num_kb = CONV ? 9 * kchunks : kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    tc::prefetch_tmap(&tmC);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < L::STAGES; ++s) {
+        tc::mbar_init(&full_bar[s], 1);
+        tc::mbar_init(&empty_bar[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        tc::mbar_init(&tmem_full_bar[b], 1);
+        tc::mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+      }
+      tc::fence_barrier_init();
+    }
+    __syncwarp();
+    tc::tmem_alloc(tmem_ptr_smem, 2 * BN);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // tile -> coordinates
+  auto tile_coords = [&](int tile, int& n0, int& m0, int& img, int& y0, int& x0) {
+    const int tn = tile % n_tiles_n;
+    int tm = tile / n_tiles_n;
+    n0 = tn * BN;
+    if (CONV) {
+      const int tx = tm % p.tiles_x;
+      tm /= p.tiles_x;
+      const int ty = tm % p.tiles_y;
+      img = tm / p.tiles_y;
+      y0 = ty * p.bh;
+      x0 = tx * p.bw;
+      m0 = (img * p.H + y0) * p.W + x0;  // output rows of a tile are contiguous in the flat [N*H*W, Cout] view
+    } else {
+      m0 = tm * BM;
+      img = y0 = x0 = 0;
+    }
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n0, m0, img, y0, x0;
+        tile_coords(tile, n0, m0, img, y0, x0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % L::STAGES;
+          const uint32_t ph = (it / L::STAGES) & 1;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          tc::mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          if (CONV) {
+            const int tap = kb / kchunks, c0 = (kb % kchunks) * BK;
+            const int ky = tap / 3, kx = tap % 3;
+            tc::tma_load_4d(sa, &tmA, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, img);
+            tc::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.Cin + c0, n0);
+          } else {
+            tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+            tc::tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(sizeof(T) == 2 && !std::is_same<T, __half>::value, BM, BN);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1, use = lt >> 1;
+        tc::mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
+        tc::fence_after_sync();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % L::STAGES;
+          const uint32_t ph = (it / L::STAGES) & 1;
+          tc::mbar_wait(&full_bar[s], ph);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t da = tc::make_desc_sw128(sa);
+          const uint64_t db = tc::make_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc::mma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          tc::mma_commit(&empty_bar[s]);
+        }
+        tc::mma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;  // TMEM lane quarter
+    const int r = q * 32 + lane;
+    uint8_t* my_staging = staging + q * (2 * 32 * 128);
+    uint32_t lt = 0, sbuf = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      int n0, m0, img, y0, x0;
+      tile_coords(tile, n0, m0, img, y0, x0);
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      tc::mbar_wait(&tmem_full_bar[buf], use & 1);
+      tc::fence_after_sync();
+      const long long m = (long long)m0 + r;
+      const bool row_ok = m < (long long)p.M;
+      const T* res_row = p.residual ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
+      const T* b2_row =
+          p.bias2 ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2 : nullptr;
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+
+      // one staging fill = 64 output columns (128 bytes per row): 64 accumulator columns, or 128 with a GLU
+      const int acc_per_fill = p.glu ? 128 : 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += acc_per_fill) {
+        uint8_t* stg = my_staging + sbuf * (32 * 128);
+        if (lane == 0) tc::tma_store_wait_read<1>();  // the store that last used this buffer has read it
+        __syncwarp();
+#pragma unroll 1
+        for (int cc = 0; cc < acc_per_fill; cc += 32) {
+          const int c = c0 + cc;
+          uint32_t raw[32];
+          tc::tmem_ld_32x32(taddr + (uint32_t)c, raw);
+          tc::tmem_ld_wait();
+          if (c + 32 >= BN) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[buf]);
+          }
+          const int col0 = n0 + c;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+#pragma unroll
+          for (int gI = 0; gI < 4; ++gI) {
+            const int col = col0 + gI * 8;
+            float* vv = v + gI * 8;
+            const bool col_ok = col < p.N;
+            if (p.bias && col_ok) {
+              float bf[8];
+              unpack8<T>(ld_cached16(reinterpret_cast<const T*>(p.bias) + col), bf);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] += bf[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i]));
+            if (b2_row && col_ok && row_ok) {
+              float bf[8];
+              unpack8<T>(ld_cached16(b2_row + col), bf);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
+            }
+            if (p.glu == 0) {
+              if (p.act) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(act_apply<T>(vv[i], p.act)));
+              }
+              if (res_row && col_ok && row_ok) {
+                float rf[8];
+                unpack8<T>(ld_cached16(res_row + col), rf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] += rf[i];
+              }
+              // 16-byte piece j of this row inside the 128-byte staging row, 128B-swizzled like the TMA expects
+              const int j = (cc >> 3) + gI;
+              *reinterpret_cast<vec8*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8<T>(vv);
+            } else {
+              T o4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float a = vv[2 * i], b = vv[2 * i + 1];
+                float o;
+                if (p.glu == 1)
+                  o = a * ss_num<T>::to_f(ss_num<T>::from_f(gelu_erf(b)));
+                else
+                  o = ss_num<T>::to_f(ss_num<T>::from_f(a / (1.f + expf(-a)))) * b;
+                o4[i] = ss_num<T>::from_f(o);
+              }
+              // 8 accumulator columns -> 4 outputs = 8 bytes; output column within the fill = (cc + gI*8) / 2
+              const int ocol = (cc + gI * 8) >> 1;          // 0..63
+              const int j = ocol >> 3, within = (ocol & 7) * 2;  // 16-byte piece, byte offset inside it
+              *reinterpret_cast<uint2*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4) + within) =
+                  *reinterpret_cast<const uint2*>(o4);
+            }
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int out_col = p.glu ? ((n0 + c0) >> 1) : (n0 + c0);
+          const int n_out = p.glu ? (p.N >> 1) : p.N;
+          if (out_col < n_out && (long long)m0 + q * 32 < (long long)p.M)
+            tc::tma_store_2d(&tmC, stg, out_col, m0 + q * 32);
+          tc::tma_store_commit();
+        }
+        sbuf ^= 1;
+      }
+    }
+    if (lane == 0) tc::tma_store_wait_all<0>();
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * BN);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side: tensor-map construction (driver entry point resolved at run time) + cache
 // ---------------------------------------------------------------------------------------------
@@ -352,6 +601,69 @@ int dispatch(int dtype, int bn, const CUtensorMap& ta, const CUtensorMap& tb, co
   }
 }
 
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+bool use_legacy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SS_GEMM_LEGACY");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <typename T, int BN, bool CONV>
+int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const GemmParams& p,
+                   int n_tiles_n, long long total_tiles, cudaStream_t s) {
+  using L = PersistLayout<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SS_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<T, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 L::TOTAL));
+    attr_set = true;
+  }
+  const int grid = (int)(total_tiles < sm_count() ? total_tiles : sm_count());
+  gemm_tc_persist_kernel<T, BN, CONV><<<grid, GEMM_THREADS, L::TOTAL, s>>>(ta, tb, tcm, p, n_tiles_n, (int)total_tiles);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool CONV>
+int dispatch_persist(int dtype, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
+                     const GemmParams& p, int n_tiles_n, long long total_tiles, cudaStream_t s) {
+  if (dtype == SS_F16) {
+    if (bn == 64) return launch_persist<__half, 64, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
+    if (bn == 128) return launch_persist<__half, 128, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
+    return launch_persist<__half, 256, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
+  } else {
+    if (bn == 64) return launch_persist<__nv_bfloat16, 64, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
+    if (bn == 128) return launch_persist<__nv_bfloat16, 128, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
+    return launch_persist<__nv_bfloat16, 256, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
+  }
+}
+
+// N tile for the persistent kernel: 128 unless the problem is narrow; GLU needs >= 128
+int pick_bn_persist(int N, int glu, int force_bn) {
+  if (force_bn == 64 || force_bn == 128 || force_bn == 256) return (glu && force_bn == 64) ? 128 : force_bn;
+  if (N <= 64 && !glu) return 64;
+  return 128;
+}
+
+int get_out_tmap(CUtensorMap* out, const void* C, int dtype, long long M, int n_out, int ldc) {
+  uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)M}, str[1] = {(uint64_t)ldc * 2};
+  uint32_t box[2] = {64, 32};
+  return get_tmap(out, C, dtype, 2, dims, str, box);
+}
+
 int pick_bn(long long m_tiles, int N, int force_bn) {
   if (force_bn == 64 || force_bn == 128 || force_bn == 256) return force_bn;
   if (N <= 64) return 64;
@@ -373,7 +685,8 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
   SS_REQUIRE(glu == 0 || (act == 0 && residual == nullptr), "GLU epilogue excludes act/residual");
   SS_REQUIRE(bias2 == nullptr || rows_per_group > 0, "bias2 needs rows_per_group");
   const long long m_tiles = (M + BM - 1) / BM;
-  const int bn = pick_bn(m_tiles, N, force_bn);
+  const bool legacy = use_legacy();
+  const int bn = legacy ? pick_bn(m_tiles, N, force_bn) : pick_bn_persist(N, glu, force_bn);
   CUtensorMap ta, tb;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)lda * 2};
@@ -401,6 +714,12 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
   p.M = M;
   p.N = N;
   p.K = K;
+  if (!legacy) {
+    CUtensorMap tcm;
+    if (int e = get_out_tmap(&tcm, C, dtype, M, glu ? N / 2 : N, ldc)) return e;
+    const int n_tiles_n = (N + bn - 1) / bn;
+    return dispatch_persist<false>(dtype, bn, ta, tb, tcm, p, n_tiles_n, m_tiles * n_tiles_n, (cudaStream_t)stream);
+  }
   dim3 grid((N + bn - 1) / bn, (unsigned)m_tiles);
   return dispatch<false>(dtype, bn, ta, tb, p, grid, (cudaStream_t)stream);
 }
@@ -416,7 +735,8 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
   int bw = W >= 128 ? 128 : W, bh = BM / bw;
   SS_REQUIRE(bw * bh == BM && W % bw == 0 && H % bh == 0, "image must tile into 128-pixel boxes");
   const long long m_tiles = (long long)Nimg * (H / bh) * (W / bw);
-  const int bn = pick_bn(m_tiles, Cout, force_bn);
+  const bool legacy = use_legacy();
+  const int bn = legacy ? pick_bn(m_tiles, Cout, force_bn) : pick_bn_persist(Cout, 0, force_bn);
   CUtensorMap ta, tb;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
@@ -451,6 +771,12 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
   p.bh = bh;
   p.tiles_x = W / bw;
   p.tiles_y = H / bh;
+  if (!legacy) {
+    CUtensorMap tcm;
+    if (int e = get_out_tmap(&tcm, y, dtype, (long long)Nimg * H * W, Cout, Cout)) return e;
+    const int n_tiles_n = (Cout + bn - 1) / bn;
+    return dispatch_persist<true>(dtype, bn, ta, tb, tcm, p, n_tiles_n, m_tiles * n_tiles_n, (cudaStream_t)stream);
+  }
   dim3 grid((Cout + bn - 1) / bn, (unsigned)m_tiles);
   return dispatch<true>(dtype, bn, ta, tb, p, grid, (cudaStream_t)stream);
 }

@@ -257,8 +257,15 @@ def scatter_rows(src, dst_rows, dst):
                _stream())
 
 
+def groupnorm_ws(N, HW, C, groups, device):
+    n = _capi.lib().ss_groupnorm_ws_floats(N, HW, C, groups)
+    return torch.empty(n, dtype=torch.float32, device=device)
+
+
 def groupnorm_nhwc(x, gamma, beta, groups, eps, silu, stats_ws, out=None):
     N, H, W, C = x.shape
+    need = _capi.lib().ss_groupnorm_ws_floats(N, H * W, C, groups)
+    assert stats_ws.numel() >= need, (stats_ws.numel(), need)
     out = torch.empty_like(x) if out is None else out
     _capi.call("ss_groupnorm_nhwc", _dt(x), _p(x), _p(out), _p(gamma), _p(beta), _p(stats_ws), N, H * W, C, groups,
                ctypes.c_float(eps), 1 if silu else 0, _stream())

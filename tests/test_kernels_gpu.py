@@ -291,7 +291,7 @@ def test_groupnorm_and_glue(cuda_dev):
             x = (torch.randn(N, H, W, C, device=cuda_dev) * 2 + 0.5).to(dt)
             g = (1 + 0.1 * torch.randn(C, device=cuda_dev)).to(dt)
             b = (0.1 * torch.randn(C, device=cuda_dev)).to(dt)
-            ws = torch.empty(2 * N * 32, device=cuda_dev, dtype=torch.float32)
+            ws = ops.groupnorm_ws(N, H * W, C, 32, cuda_dev)
             for silu in (False, True):
                 y = ops.groupnorm_nhwc(x, g, b, 32, 1e-5, silu, ws)
                 ref = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), 32, g.float(), b.float(), 1e-5)
