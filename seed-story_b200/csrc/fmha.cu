@@ -10,6 +10,8 @@
 //
 // v1 uses mma.sync m16n8k16 (64 query rows x 64 keys per CTA iteration); the tcgen05 version with S/P
 // in TMEM is the planned replacement.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -276,6 +278,20 @@ int launch_fmha(const FmhaParams& p, cudaStream_t s) {
 
 }  // namespace
 
+int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, int B, int H, int Lq, int Lk, int D,
+                        long long q_sb, long long q_sl, long long q_sh, long long k_sb, long long k_sl, long long k_sh,
+                        long long v_sb, long long v_sl, long long v_sh, long long o_sb, long long o_sl, long long o_sh,
+                        float scale, int causal, cudaStream_t stream);
+
+static bool fmha_legacy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SS_FMHA_LEGACY");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 SS_API int ss_fmha_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int Lq, int Lk, int D,
                        long long q_sb, long long q_sl, long long q_sh, long long k_sb, long long k_sl, long long k_sh,
                        long long v_sb, long long v_sl, long long v_sh, long long o_sb, long long o_sl, long long o_sh,
@@ -285,6 +301,12 @@ SS_API int ss_fmha_f16(const void* q, const void* k, const void* v, void* out, i
   SS_REQUIRE(q_sl % 8 == 0 && k_sl % 8 == 0 && v_sl % 8 == 0 && o_sl % 2 == 0, "token strides must keep 16-byte rows");
   SS_REQUIRE(q_sh % 8 == 0 && k_sh % 8 == 0 && v_sh % 8 == 0, "head strides must keep 16-byte rows");
   if (B == 0 || H == 0 || Lq == 0) return 0;
+  if (!fmha_legacy() && page_table == nullptr && kv_lens == nullptr && Lq >= 64 && k_sb == v_sb) {
+    // tcgen05 path (S/PV accumulators in TMEM); -1 = layout not expressible as row-matrix views
+    const int rc = ss_internal_fmha_tc(q, k, v, out, B, H, Lq, Lk, D, q_sb, q_sl, q_sh, k_sb, k_sl, k_sh, v_sb, v_sl, v_sh,
+                                       o_sb, o_sl, o_sh, scale, causal, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   FmhaParams p;
   p.q = (const __half*)q;
   p.k = (const __half*)k;

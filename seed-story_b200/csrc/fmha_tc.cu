@@ -1,0 +1,355 @@
+// Fused attention on the 5th-gen tensor cores (tcgen05 + TMEM), fp16, head_dim 64 / 128.
+//   S = Q K^T     tcgen05.mma  M=128 (queries) x N=128 (keys) x K=D, operands from TMA-staged shared memory,
+//                 accumulator in TMEM (two S buffers: the MMA of tile j+1 overlaps the softmax of tile j)
+//   softmax       128 threads, ONE QUERY ROW PER THREAD (tcgen05.ld 32x32b gives each lane a full row slice, so
+//                 row max / row sum need no shuffles); exp2 with the scale folded in; P written as fp16 into
+//                 128B-swizzled shared memory
+//   PV = P V      tcgen05.mma  M=128 x N=D x K=128 with V as an MN-major B operand straight from the [key][d]
+//                 layout TMA delivers; the per-tile product is read back and folded into the fp32 running output
+//                 held in registers (O = O * corr + PV), so no TMEM rescale pass is needed
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = softmax + output (one row per thread).
+// Same mask semantics as fmha.cu: causal diagonal anchored bottom-right (xformers LowerTriangularFromBottomRightMask,
+// modeling_llama_xformer.py:289-295), keys >= Lk masked.  Operands are row-matrix views (token rows, heads side by
+// side in a row) so fused QKV buffers are consumed in place.
+#include <cstring>
+
+#include "tc.cuh"
+
+namespace {
+
+constexpr int FT_BM = 128, FT_BN = 128, FT_THREADS = 192;
+
+struct FtParams {
+  __half* o;
+  long long o_sb, o_sl, o_sh;
+  int H, Lq, Lk;
+  int q_rows_per_batch, k_rows_per_batch;  // 0 => operand is broadcast over the batch
+  int q_col_per_head, k_col_per_head, v_col_per_head;
+  int q_col0, k_col0, v_col0;
+  float scale_log2;
+  int causal;
+};
+
+template <int D>
+struct FtSmem {
+  static constexpr int ATOM = 128 * 128;            // [128 rows][64 x 16-bit] = 16 KB
+  static constexpr int Q_BYTES = (D / 64) * ATOM;
+  static constexpr int KV_BYTES = (D / 64) * ATOM;  // K tile or V tile
+  static constexpr int P_BYTES = 2 * ATOM;
+  static constexpr int STAGES = 2;
+  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + 1024 + 256;
+};
+
+// MN-major B operand (V as [key][d] rows of 128 bytes, 128B swizzle): SBO = 8 key rows * 128 B, LBO = distance between
+// 64-wide d atoms (128 keys * 128 B)
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int D>
+__global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                const __grid_constant__ CUtensorMap tmK,
+                                                                const __grid_constant__ CUtensorMap tmV,
+                                                                const FtParams p) {
+  using S = FtSmem<D>;
+  extern __shared__ uint8_t ft_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + S::Q_BYTES;                       // stage s: K at s*2*KV, V right after
+  uint8_t* sP = sKV + S::STAGES * 2 * S::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + S::P_BYTES);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;      // [2]
+  uint64_t* s_empty = bars + 7;     // [2]
+  uint64_t* p_full = bars + 9;      // 1
+  uint64_t* pv_full = bars + 10;    // 1
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * FT_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int Lq = p.Lq, Lk = p.Lk;
+  const int shift = Lk - Lq;
+  int n_end = Lk;
+  if (p.causal) n_end = min(Lk, m0 + FT_BM + shift);
+  const int ntiles = (n_end + FT_BN - 1) / FT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmQ);
+    tc::prefetch_tmap(&tmK);
+    tc::prefetch_tmap(&tmV);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      tc::mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        tc::mbar_init(&kv_full[i], 1);
+        tc::mbar_init(&kv_empty[i], 1);
+        tc::mbar_init(&s_full[i], 1);
+        tc::mbar_init(&s_empty[i], 4);
+      }
+      tc::mbar_init(p_full, 4);
+      tc::mbar_init(pv_full, 1);
+      tc::fence_barrier_init();
+    }
+    __syncwarp();
+    tc::tmem_alloc(tmem_ptr_smem, 512);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_S0 = tmem_base, tmem_PV = tmem_base + 256;
+
+  if (ntiles == 0) {
+    // nothing visible (only possible for degenerate causal shapes): write zeros
+    if (warp >= 2) {
+      const int r = (warp & 3) * 32 + lane;
+      if (m0 + r < Lq) {
+        __half* orow = p.o + b * p.o_sb + (long long)(m0 + r) * p.o_sl + h * p.o_sh;
+        for (int d = 0; d < D; ++d) orow[d] = __float2half_rn(0.f);
+      }
+    }
+  } else if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int qrow0 = b * p.q_rows_per_batch + m0;
+      tc::mbar_expect_tx(q_full, S::Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < D / 64; ++a)
+        tc::tma_load_2d(sQ + a * S::ATOM, &tmQ, q_full, p.q_col0 + h * p.q_col_per_head + a * 64, qrow0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        tc::mbar_wait(&kv_empty[s], ph ^ 1);
+        uint8_t* sK = sKV + s * 2 * S::KV_BYTES;
+        uint8_t* sV = sK + S::KV_BYTES;
+        const int krow0 = b * p.k_rows_per_batch + j * FT_BN;
+        tc::mbar_expect_tx(&kv_full[s], 2 * S::KV_BYTES);
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a) {
+          tc::tma_load_2d(sK + a * S::ATOM, &tmK, &kv_full[s], p.k_col0 + h * p.k_col_per_head + a * 64, krow0);
+          tc::tma_load_2d(sV + a * S::ATOM, &tmV, &kv_full[s], p.v_col0 + h * p.v_col_per_head + a * 64, krow0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = tc::make_idesc(0, FT_BM, FT_BN);               // A, B K-major
+      constexpr uint32_t idesc_pv = tc::make_idesc(0, FT_BM, D) | (1u << 16);      // B (V) MN-major
+      const uint32_t aQ = tc::smem_u32(sQ), aP = tc::smem_u32(sP);
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        tc::mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc::mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tc::fence_after_sync();
+        const uint32_t aK = tc::smem_u32(sKV + s * 2 * S::KV_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * S::ATOM + (kk & 3) * 32;
+          tc::mma_f16_ss(tmem_S0 + (j & 1) * 128, tc::make_desc_sw128(aQ + off), tc::make_desc_sw128(aK + off), idesc_qk,
+                         kk != 0);
+        }
+        tc::mma_commit(&s_full[j & 1]);
+      };
+      tc::mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_qk(j + 1);
+        tc::mbar_wait(p_full, j & 1);  // P_j is in shared memory (and PV_{j-1} has been consumed)
+        tc::fence_after_sync();
+        const int s = j & 1;
+        const uint32_t aV = tc::smem_u32(sKV + s * 2 * S::KV_BYTES + S::KV_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < FT_BN / 16; ++kk) {
+          const uint64_t da = tc::make_desc_sw128(aP + (kk >> 2) * S::ATOM + (kk & 3) * 32);
+          const uint64_t db = make_desc_mn_sw128(aV + kk * 16 * 128, S::ATOM);
+          tc::mma_f16_ss(tmem_PV, da, db, idesc_pv, kk != 0);
+        }
+        tc::mma_commit(&kv_empty[s]);  // K_j / V_j no longer needed
+        tc::mma_commit(pv_full);
+      }
+    }
+  } else {
+    // ================= softmax + output: one query row per thread =================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int qrow = m0 + r;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float o_acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    auto add_pv = [&]() {
+#pragma unroll
+      for (int c = 0; c < D; c += 32) {
+        uint32_t raw[32];
+        tc::tmem_ld_32x32(tmem_PV + lane_off + c, raw);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c + i] += __uint_as_float(raw[i]);
+      }
+    };
+
+    for (int j = 0; j < ntiles; ++j) {
+      const uint32_t tS = tmem_S0 + (j & 1) * 128 + lane_off;
+      const int key0 = j * FT_BN;
+      const bool need_mask = (key0 + FT_BN > Lk) || (p.causal && (key0 + FT_BN - 1 > m0 + q * 32 + shift));
+      const int key_lim = p.causal ? min(Lk - 1, qrow + shift) : (Lk - 1);  // last visible key for this row
+      tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc::fence_after_sync();
+      // pass 1: row maximum
+      float mx = m_run;
+#pragma unroll 1
+      for (int c = 0; c < FT_BN; c += 32) {
+        uint32_t raw[32];
+        tc::tmem_ld_32x32(tS + c, raw);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float sv = __uint_as_float(raw[i]);
+          if (need_mask && key0 + c + i > key_lim) sv = -INFINITY;
+          mx = fmaxf(mx, sv);
+        }
+      }
+      const float msc = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
+      const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2 - msc);
+      // fold in the previous tile's P V (it was computed relative to the previous maximum), then rescale
+      if (j > 0) {
+        tc::mbar_wait(pv_full, (j - 1) & 1);
+        tc::fence_after_sync();
+        add_pv();
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) o_acc[i] *= corr;
+      l_run *= corr;
+      m_run = mx;
+      // pass 2: probabilities -> shared memory (fp16, 128B-swizzled atoms of 64 keys)
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < FT_BN; c += 32) {
+        uint32_t raw[32];
+        tc::tmem_ld_32x32(tS + c, raw);
+        tc::tmem_ld_wait();
+        if (c + 32 >= FT_BN) {  // last read of S_j: the MMA warp may overwrite this buffer with S_{j+2}
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&s_empty[j & 1]);
+        }
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a = __uint_as_float(raw[i]), bb = __uint_as_float(raw[i + 1]);
+          if (need_mask && key0 + c + i > key_lim) a = -INFINITY;
+          if (need_mask && key0 + c + i + 1 > key_lim) bb = -INFINITY;
+          const float pa = exp2f(a * p.scale_log2 - msc), pb = exp2f(bb * p.scale_log2 - msc);
+          lsum += pa + pb;
+          __half2 hh = __floats2half2_rn(pa, pb);
+          packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        uint8_t* atom = sP + (c >> 6) * S::ATOM + r * 128;
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const int jj = ((c & 63) >> 3) + g4;  // 16-byte piece within the 128-byte row
+          *reinterpret_cast<uint4*>(atom + ((jj ^ (r & 7)) << 4)) =
+              make_uint4(packed[4 * g4], packed[4 * g4 + 1], packed[4 * g4 + 2], packed[4 * g4 + 3]);
+        }
+      }
+      l_run += lsum;
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(p_full);
+    }
+    // last tile's P V
+    tc::mbar_wait(pv_full, (ntiles - 1) & 1);
+    tc::fence_after_sync();
+    add_pv();
+    if (qrow < Lq) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __half* orow = p.o + b * p.o_sb + (long long)qrow * p.o_sl + h * p.o_sh;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = o_acc[c + i] * inv;
+        *reinterpret_cast<vec8*>(orow + c) = pack8<__half>(f);
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// tensor-map helper (defined in gemm_tc.cu)
+}  // namespace
+
+int ss_internal_get_tmap(CUtensorMap* out, const void* ptr, int dtype, int rank, const uint64_t* dims,
+                         const uint64_t* strides, const uint32_t* box);
+
+namespace {
+template <int D>
+int launch_ft(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FtParams& p, int B,
+              cudaStream_t s) {
+  using S = FtSmem<D>;
+  static bool attr = false;
+  if (!attr) {
+    SS_CUDA(cudaFuncSetAttribute(fmha_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr = true;
+  }
+  dim3 grid((p.Lq + FT_BM - 1) / FT_BM, p.H, B);
+  fmha_tc_kernel<D><<<grid, FT_THREADS, S::TOTAL, s>>>(tq, tk, tv, p);
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
+// Returns 0 on success, -1 when the operand layout is not expressible as row-matrix views (caller falls back to
+// the mma.sync kernel), > 0 on error.
+int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, int B, int H, int Lq, int Lk, int D,
+                        long long q_sb, long long q_sl, long long q_sh, long long k_sb, long long k_sl, long long k_sh,
+                        long long v_sb, long long v_sl, long long v_sh, long long o_sb, long long o_sl, long long o_sh,
+                        float scale, int causal, cudaStream_t stream) {
+  if (D != 64 && D != 128) return -1;
+  // heads must sit side by side inside a token row, batches must be stacked row blocks (or broadcast)
+  auto ok = [&](long long sb, long long sl, long long sh, int L) {
+    return sl % 8 == 0 && sh % 8 == 0 && sh * (H - 1) + D <= sl && (sb == 0 || sb == (long long)L * sl);
+  };
+  if (!ok(q_sb, q_sl, q_sh, Lq) || !ok(k_sb, k_sl, k_sh, Lk) || !ok(v_sb, v_sl, v_sh, Lk)) return -1;
+  if (k_sb != v_sb && !(k_sb == 0 || v_sb == 0)) return -1;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) return -1;
+  if (o_sl % 8 != 0 || o_sh % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return -1;
+  CUtensorMap tq, tk, tv;
+  auto mk = [&](CUtensorMap* tm, const void* ptr, long long sb, long long sl, int L) {
+    const uint64_t rows = (uint64_t)(sb == 0 ? L : (long long)B * L);
+    uint64_t dims[2] = {(uint64_t)sl, rows}, str[1] = {(uint64_t)sl * 2};
+    uint32_t box[2] = {64, 128};
+    return ss_internal_get_tmap(tm, ptr, SS_F16, 2, dims, str, box);
+  };
+  if (int e = mk(&tq, q, q_sb, q_sl, Lq)) return e;
+  if (int e = mk(&tk, k, k_sb, k_sl, Lk)) return e;
+  if (int e = mk(&tv, v, v_sb, v_sl, Lk)) return e;
+  FtParams p;
+  memset(&p, 0, sizeof(p));
+  p.o = (__half*)out;
+  p.o_sb = o_sb; p.o_sl = o_sl; p.o_sh = o_sh;
+  p.H = H; p.Lq = Lq; p.Lk = Lk;
+  p.q_rows_per_batch = q_sb == 0 ? 0 : Lq;
+  p.k_rows_per_batch = k_sb == 0 ? 0 : Lk;
+  p.q_col_per_head = (int)q_sh; p.k_col_per_head = (int)k_sh; p.v_col_per_head = (int)v_sh;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  if (D == 64) return launch_ft<64>(tq, tk, tv, p, B, stream);
+  return launch_ft<128>(tq, tk, tv, p, B, stream);
+}

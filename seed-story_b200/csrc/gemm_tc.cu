@@ -574,6 +574,16 @@ int get_tmap(CUtensorMap* out, const void* ptr, int dtype, int rank, const uint6
   return 0;
 }
 
+}  // namespace
+
+// shared with fmha_tc.cu
+int ss_internal_get_tmap(CUtensorMap* out, const void* ptr, int dtype, int rank, const uint64_t* dims,
+                         const uint64_t* strides, const uint32_t* box) {
+  return get_tmap(out, ptr, dtype, rank, dims, strides, box);
+}
+
+namespace {
+
 template <typename T, int BN, bool CONV>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t s) {
   using L = SmemLayout<BN>;

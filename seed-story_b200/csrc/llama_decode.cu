@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
 
   float c[4] = {0.f, 0.f, 0.f, 0.f};
   int kb = warp;
+  pdl_trigger();
+  bool first = true;
   for (; kb + (SG_UNROLL - 1) * SG_WARPS < nkb; kb += SG_UNROLL * SG_WARPS) {
     vec8 a_lo[SG_UNROLL], a_hi[SG_UNROLL], xb[SG_UNROLL];
 #pragma unroll
@@ -53,6 +55,10 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
       const int off = (kb + u * SG_WARPS) << 5;
       a_lo[u] = ld_stream16(w_lo + off);
       a_hi[u] = ld_stream16(w_hi + off);
+    }
+    if (first) {  // weights are constants: the first batch is in flight before we wait for the producer of x
+      pdl_wait();
+      first = false;
     }
 #pragma unroll
     for (int u = 0; u < SG_UNROLL; ++u) {
@@ -65,6 +71,7 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
       mma16816(c, a_lo[u].z, a_hi[u].z, a_lo[u].w, a_hi[u].w, xb[u].z, xb[u].w);
     }
   }
+  if (first) pdl_wait();
   for (; kb < nkb; kb += SG_WARPS) {
     const int off = kb << 5;
     const vec8 a_lo = ld_stream16(w_lo + off), a_hi = ld_stream16(w_hi + off);
@@ -125,14 +132,17 @@ SS_API int ss_skinny_gemm_f16(const void* x, int ldx, const void* W, void* y, in
   __half* yp = (__half*)y;
   switch (epilogue) {
     case EPI_NONE:
-      skinny_gemm_kernel<EPI_NONE><<<grid, SG_WARPS * 32, 0, s>>>(xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr);
+      SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_NONE>, dim3(grid), dim3(SG_WARPS * 32), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp,
+                             ldr));
       break;
     case EPI_RESIDUAL:
       SS_REQUIRE(residual != nullptr, "residual epilogue needs a residual pointer");
-      skinny_gemm_kernel<EPI_RESIDUAL><<<grid, SG_WARPS * 32, 0, s>>>(xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr);
+      SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_RESIDUAL>, dim3(grid), dim3(SG_WARPS * 32), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp,
+                             ldr));
       break;
     case EPI_SWIGLU:
-      skinny_gemm_kernel<EPI_SWIGLU><<<grid, SG_WARPS * 32, 0, s>>>(xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr);
+      SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_SWIGLU>, dim3(grid), dim3(SG_WARPS * 32), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp,
+                             ldr));
       break;
     default:
       SS_FAIL("unknown epilogue");
@@ -163,6 +173,8 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const __half* __restri
                                                           const int* __restrict__ page_table, int max_pages,
                                                           const __half* __restrict__ cos_t,
                                                           const __half* __restrict__ sin_t, int H, int D) {
+  pdl_trigger();
+  pdl_wait();
   const int tok = blockIdx.x;
   const int seq = tok_seq[tok], pos = tok_pos[tok], slot = tok_slot[tok];
   const int page = page_table[(size_t)seq * max_pages + slot / KV_PAGE];
@@ -199,9 +211,9 @@ SS_API int ss_rope_kv_append_f16(const void* qkv, int ld_qkv, void* q_out, void*
                                  int H, int D, void* stream) {
   SS_REQUIRE(D % 2 == 0, "head dim must be even");
   if (ntok == 0) return 0;
-  rope_append_kernel<<<ntok, 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, ld_qkv, (__half*)q_out, (__half*)kcache, (__half*)vcache, tok_seq, tok_pos, tok_slot,
-      page_table, max_pages, (const __half*)cos_table, (const __half*)sin_table, H, D);
+  SS_CUDA(ss::launch_pdl(rope_append_kernel, dim3(ntok), dim3(256), 0, (cudaStream_t)stream, (const __half*)qkv, ld_qkv,
+                         (__half*)q_out, (__half*)kcache, (__half*)vcache, tok_seq, tok_pos, tok_slot, page_table,
+                         max_pages, (const __half*)cos_table, (const __half*)sin_table, H, D));
   SS_LAUNCH_CHECK();
   return 0;
 }
@@ -222,6 +234,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
   __shared__ float sc[AD_MAX_CHUNK];
   __shared__ float red[32];
   __shared__ __align__(16) __half qs[D];
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, s = blockIdx.z;
   const int n = seq_lens[b];
   const int npages = (n + KV_PAGE - 1) / KV_PAGE;
@@ -295,6 +309,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
 __global__ void __launch_bounds__(128) attn_decode_combine_kernel(const float* __restrict__ part,
                                                                   __half* __restrict__ out, int H, int S) {
   constexpr int D = 128;
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
   const float* p = part + ((size_t)b * H + h) * S * (D + 2);
   float m = -INFINITY;
@@ -318,11 +334,11 @@ SS_API int ss_attn_decode_paged_f16(const void* q, const void* kcache, const voi
              "too few splits for max_pages (each split holds <= 1024 tokens)");
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  attn_decode_split_kernel<<<dim3(H, B, splits), AD_THREADS, 0, s>>>(
-      (const __half*)q, (const __half*)kcache, (const __half*)vcache, seq_lens, page_table, max_pages, workspace, H,
-      splits, scale);
-  SS_LAUNCH_CHECK();
-  attn_decode_combine_kernel<<<dim3(H, B), 128, 0, s>>>(workspace, (__half*)out, H, splits);
+  SS_CUDA(ss::launch_pdl(attn_decode_split_kernel, dim3(H, B, splits), dim3(AD_THREADS), 0, s, (const __half*)q,
+                         (const __half*)kcache, (const __half*)vcache, seq_lens, page_table, max_pages, workspace, H,
+                         splits, scale));
+  SS_CUDA(ss::launch_pdl(attn_decode_combine_kernel, dim3(H, B), dim3(128), 0, s, (const float*)workspace, (__half*)out,
+                         H, splits));
   SS_LAUNCH_CHECK();
   return 0;
 }

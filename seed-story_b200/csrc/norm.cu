@@ -11,6 +11,8 @@ __global__ void __launch_bounds__(256) rmsnorm_f16_kernel(const __half* __restri
                                                           const __half* __restrict__ w, __half* __restrict__ y,
                                                           int ldy, int K, float eps) {
   __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;
   const __half* xr = x + (size_t)row * ldx;
   __half* yr = y + (size_t)row * ldy;
@@ -55,9 +57,11 @@ SS_API int ss_rmsnorm_f16(const void* x, int ldx, const void* weight, void* y, i
   cudaStream_t s = (cudaStream_t)stream;
   const int nvec = K / 8;
   if (nvec <= 256 * 2)
-    rmsnorm_f16_kernel<2><<<rows, 256, 0, s>>>((const __half*)x, ldx, (const __half*)weight, (__half*)y, ldy, K, eps);
+    SS_CUDA(ss::launch_pdl(rmsnorm_f16_kernel<2>, dim3(rows), dim3(256), 0, s, (const __half*)x, ldx,
+                           (const __half*)weight, (__half*)y, ldy, K, eps));
   else
-    rmsnorm_f16_kernel<6><<<rows, 256, 0, s>>>((const __half*)x, ldx, (const __half*)weight, (__half*)y, ldy, K, eps);
+    SS_CUDA(ss::launch_pdl(rmsnorm_f16_kernel<6>, dim3(rows), dim3(256), 0, s, (const __half*)x, ldx,
+                           (const __half*)weight, (__half*)y, ldy, K, eps));
   SS_LAUNCH_CHECK();
   return 0;
 }

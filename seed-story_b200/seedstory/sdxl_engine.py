@@ -171,7 +171,11 @@ class UNetEngine:
         self.ctx_len = ctx.shape[1]
         for t2d in self._all_t2d():
             for b in t2d.blocks:
-                b["kv_ctx"] = ops.gemm(ctx2, b["kv2"])  # [2*T, 2C]: k | v
+                # persistent buffers: the captured CUDA graph reads these addresses on every replay
+                if b["kv_ctx"] is None or b["kv_ctx"].shape[0] != ctx2.shape[0]:
+                    assert self._graph is None, "context length changed after graph capture"
+                    b["kv_ctx"] = torch.empty((ctx2.shape[0], b["kv2"].shape[0]), dtype=F16, device=dev)
+                ops.gemm(ctx2, b["kv2"], out=b["kv_ctx"])  # [2*T, 2C]: k | v
         S = len(timesteps)
         t_emb = timestep_embedding(np.repeat(np.asarray(timesteps, dtype=np.float32), 2), self.ch[0]).to(dev, F16)
         e = ops.gemm(t_emb, self.time_mlp[0], bias=self.time_mlp[1], act=ops.ACT_SILU)
