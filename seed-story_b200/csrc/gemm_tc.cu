@@ -249,10 +249,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
 // =============================================================================================
 template <int BN>
 struct PersistLayout {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
+  // a stage holds KATOMS k-atoms of 64 elements: wide stages amortise the per-stage barrier round trip of the
+  // single MMA-issuing thread when the N tile (and with it the tensor-core time per atom) is small
+  static constexpr int KATOMS = (BN == 256) ? 1 : 2;
+  static constexpr int A_BYTES = BM * BK * 2;   // per atom
+  static constexpr int B_BYTES = BN * BK * 2;   // per atom
+  static constexpr int STAGE_BYTES = KATOMS * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int STAGING_BYTES = 4 /*warps*/ * 2 /*bufs*/ * 32 * 128;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -276,7 +279,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kchunks = CONV ? (p.Cin / BK) : ((p.K + BK - 1) / BK);
-  const int num_kb = CONV ? 9 * kchunks : kchunks;
+  const int num_atoms = CONV ? 9 * kchunks : kchunks;                  // 64-wide k atoms per tile
+  const int num_kb = (num_atoms + L::KATOMS - 1) / L::KATOMS;          // pipeline stages per tile
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -333,17 +337,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
           const int s = it % L::STAGES;
           const uint32_t ph = (it / L::STAGES) & 1;
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * L::STAGE_BYTES;
-          uint8_t* sb = sa + L::A_BYTES;
-          tc::mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-          if (CONV) {
-            const int tap = kb / kchunks, c0 = (kb % kchunks) * BK;
-            const int ky = tap / 3, kx = tap % 3;
-            tc::tma_load_4d(sa, &tmA, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, img);
-            tc::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.Cin + c0, n0);
-          } else {
-            tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
-            tc::tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+          uint8_t* stage = smem + s * L::STAGE_BYTES;
+          const int na = min(L::KATOMS, num_atoms - kb * L::KATOMS);
+          tc::mbar_expect_tx(&full_bar[s], na * (L::A_BYTES + L::B_BYTES));
+          for (int a = 0; a < na; ++a) {
+            const int atom = kb * L::KATOMS + a;
+            uint8_t* sa = stage + a * (L::A_BYTES + L::B_BYTES);
+            uint8_t* sb = sa + L::A_BYTES;
+            if (CONV) {
+              const int tap = atom / kchunks, c0 = (atom % kchunks) * BK;
+              const int ky = tap / 3, kx = tap % 3;
+              tc::tma_load_4d(sa, &tmA, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, img);
+              tc::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.Cin + c0, n0);
+            } else {
+              tc::tma_load_2d(sa, &tmA, &full_bar[s], atom * BK, m0);
+              tc::tma_load_2d(sb, &tmB, &full_bar[s], atom * BK, n0);
+            }
           }
         }
       }
@@ -363,12 +372,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
           const uint32_t ph = (it / L::STAGES) & 1;
           tc::mbar_wait(&full_bar[s], ph);
           tc::fence_after_sync();
-          const uint32_t sa = tc::smem_u32(smem + s * L::STAGE_BYTES);
-          const uint64_t da = tc::make_desc_sw128(sa);
-          const uint64_t db = tc::make_desc_sw128(sa + L::A_BYTES);
+          const int na = min(L::KATOMS, num_atoms - kb * L::KATOMS);
+          for (int a = 0; a < na; ++a) {
+            const uint32_t sa = tc::smem_u32(smem + s * L::STAGE_BYTES + a * (L::A_BYTES + L::B_BYTES));
+            const uint64_t da = tc::make_desc_sw128(sa);
+            const uint64_t db = tc::make_desc_sw128(sa + L::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc::mma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)
+              tc::mma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | a | k) != 0);
+          }
           tc::mma_commit(&empty_bar[s]);
         }
         tc::mma_commit(&tmem_full_bar[buf]);
@@ -665,7 +677,9 @@ int dispatch_persist(int dtype, int bn, const CUtensorMap& ta, const CUtensorMap
 int pick_bn_persist(int N, int glu, int force_bn) {
   if (force_bn == 64 || force_bn == 128 || force_bn == 256) return (glu && force_bn == 64) ? 128 : force_bn;
   if (N <= 64 && !glu) return 64;
-  return 128;
+  // wider N tiles halve the B-operand traffic and the MMA issue overhead; take 256 unless it pads N much more
+  const int pad256 = (N + 255) / 256 * 256, pad128 = (N + 127) / 128 * 128;
+  return (pad256 * 100 <= pad128 * 108) ? 256 : 128;
 }
 
 int get_out_tmap(CUtensorMap* out, const void* C, int dtype, long long M, int n_out, int ldc) {

@@ -24,80 +24,78 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
 }
 
 constexpr int SG_WARPS = 8;
-constexpr int SG_UNROLL = 4;
+constexpr int SG_UNROLL = 8;   // k-blocks (32 wide) per register batch; two batches are in flight per warp
+constexpr int SG_ROWS = 8;     // weight rows per CTA
 
-// One CTA = one 16-row tile of W; the 8 warps interleave over 32-wide k-blocks and their partial
-// 16x8 accumulators are reduced through shared memory.
+// One CTA = 8 rows of W.  The weight rows are the B operand (n = row), the <= 8 activation rows the A operand
+// (m = batch index, rows 8..15 zero), so a lane streams ONE 16-byte piece of one weight row per 32-wide k-block;
+// the 8 warps interleave over k-blocks, keep two register batches of loads in flight (software pipeline) and
+// reduce their 8x8 partial results through shared memory.
 template <int EPI>
 __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half* __restrict__ x, int ldx,
                                                                     const __half* __restrict__ W,
                                                                     __half* __restrict__ y, int ldy, int B, int N,
                                                                     int K, const __half* __restrict__ res, int ldr) {
-  __shared__ float part[SG_WARPS][16][8];
+  __shared__ float part[SG_WARPS][8][8];  // [warp][batch][row]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int row0 = blockIdx.x * 16;
-  const int r_lo = min(row0 + g, N - 1), r_hi = min(row0 + g + 8, N - 1);  // clamp: tail rows are recomputed, not stored
-  const __half* w_lo = W + (size_t)r_lo * K + t * 8;
-  const __half* w_hi = W + (size_t)r_hi * K + t * 8;
+  const int row0 = blockIdx.x * SG_ROWS;
+  const int r_w = min(row0 + g, N - 1);  // clamp: tail rows are recomputed, never stored
+  const __half* wp = W + (size_t)r_w * K + t * 8;
   const __half* xg = x + (size_t)min(g, B - 1) * ldx + t * 8;
   const bool xvalid = g < B;
   const int nkb = K >> 5;
+  const int my_n = (nkb - warp + SG_WARPS - 1) / SG_WARPS;  // k-blocks owned by this warp: warp, warp+8, ...
 
   float c[4] = {0.f, 0.f, 0.f, 0.f};
-  int kb = warp;
   pdl_trigger();
-  bool first = true;
-  for (; kb + (SG_UNROLL - 1) * SG_WARPS < nkb; kb += SG_UNROLL * SG_WARPS) {
-    vec8 a_lo[SG_UNROLL], a_hi[SG_UNROLL], xb[SG_UNROLL];
+  vec8 wa[SG_UNROLL], wb[SG_UNROLL];
+  auto load_batch = [&](vec8* dst, int first) {
 #pragma unroll
     for (int u = 0; u < SG_UNROLL; ++u) {
-      const int off = (kb + u * SG_WARPS) << 5;
-      a_lo[u] = ld_stream16(w_lo + off);
-      a_hi[u] = ld_stream16(w_hi + off);
+      const int i = first + u;
+      dst[u] = (i < my_n) ? ld_stream16(wp + ((size_t)(warp + i * SG_WARPS) << 5)) : vec8{0u, 0u, 0u, 0u};
     }
-    if (first) {  // weights are constants: the first batch is in flight before we wait for the producer of x
-      pdl_wait();
-      first = false;
-    }
+  };
+  auto compute_batch = [&](const vec8* src, int first) {
+    vec8 xb[SG_UNROLL];
 #pragma unroll
     for (int u = 0; u < SG_UNROLL; ++u) {
-      const int off = (kb + u * SG_WARPS) << 5;
-      xb[u] = xvalid ? ld_cached16(xg + off) : vec8{0u, 0u, 0u, 0u};
+      const int i = first + u;
+      xb[u] = (xvalid && i < my_n) ? ld_cached16(xg + ((size_t)(warp + i * SG_WARPS) << 5)) : vec8{0u, 0u, 0u, 0u};
     }
 #pragma unroll
     for (int u = 0; u < SG_UNROLL; ++u) {
-      mma16816(c, a_lo[u].x, a_hi[u].x, a_lo[u].y, a_hi[u].y, xb[u].x, xb[u].y);
-      mma16816(c, a_lo[u].z, a_hi[u].z, a_lo[u].w, a_hi[u].w, xb[u].z, xb[u].w);
+      // same k permutation on both operands: piece j of the 16-byte vector feeds k-pairs (2t,2t+1)/(2t+8,2t+9)
+      mma16816(c, xb[u].x, 0u, xb[u].y, 0u, src[u].x, src[u].y);
+      mma16816(c, xb[u].z, 0u, xb[u].w, 0u, src[u].z, src[u].w);
     }
+  };
+  load_batch(wa, 0);  // weights are constants: in flight before we wait for the producer of x
+  pdl_wait();
+  for (int first = 0; first < my_n; first += 2 * SG_UNROLL) {
+    load_batch(wb, first + SG_UNROLL);
+    compute_batch(wa, first);
+    load_batch(wa, first + 2 * SG_UNROLL);
+    compute_batch(wb, first + SG_UNROLL);
   }
-  if (first) pdl_wait();
-  for (; kb < nkb; kb += SG_WARPS) {
-    const int off = kb << 5;
-    const vec8 a_lo = ld_stream16(w_lo + off), a_hi = ld_stream16(w_hi + off);
-    const vec8 xb = xvalid ? ld_cached16(xg + off) : vec8{0u, 0u, 0u, 0u};
-    mma16816(c, a_lo.x, a_hi.x, a_lo.y, a_hi.y, xb.x, xb.y);
-    mma16816(c, a_lo.z, a_hi.z, a_lo.w, a_hi.w, xb.z, xb.w);
-  }
-  // C fragment: c0,c1 -> (row g, col 2t,2t+1); c2,c3 -> (row g+8, col 2t,2t+1); col = batch index
+  // C fragment: c0,c1 -> (batch g, rows 2t,2t+1); c2,c3 belong to the zero half of A
   part[warp][g][2 * t] = c[0];
   part[warp][g][2 * t + 1] = c[1];
-  part[warp][g + 8][2 * t] = c[2];
-  part[warp][g + 8][2 * t + 1] = c[3];
   __syncthreads();
 
   if (EPI == EPI_SWIGLU) {
     // tile rows (2j, 2j+1) are (gate_j, up_j): the host interleaves gate/up rows pairwise, the same
     // packing the tensor-core GEMM's GLU epilogue consumes
-    if (threadIdx.x < 64) {
-      const int r = threadIdx.x >> 3, n = threadIdx.x & 7;
+    if (threadIdx.x < 32) {
+      const int n = threadIdx.x >> 2, j = threadIdx.x & 3;
       float gate = 0.f, up = 0.f;
 #pragma unroll
       for (int w = 0; w < SG_WARPS; ++w) {
-        gate += part[w][2 * r][n];
-        up += part[w][2 * r + 1][n];
+        gate += part[w][n][2 * j];
+        up += part[w][n][2 * j + 1];
       }
-      const int out_col = blockIdx.x * 8 + r;
+      const int out_col = blockIdx.x * 4 + j;
       if (n < B && out_col < (N >> 1)) {
         const __half gh = __float2half_rn(gate);
         const float gf = __half2float(gh);
@@ -106,11 +104,11 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
       }
     }
   } else {
-    if (threadIdx.x < 128) {
-      const int r = threadIdx.x >> 3, n = threadIdx.x & 7;
+    if (threadIdx.x < 64) {
+      const int n = threadIdx.x >> 3, r = threadIdx.x & 7;
       float acc = 0.f;
 #pragma unroll
-      for (int w = 0; w < SG_WARPS; ++w) acc += part[w][r][n];
+      for (int w = 0; w < SG_WARPS; ++w) acc += part[w][n][r];
       const int row = row0 + r;
       if (n < B && row < N) {
         __half o = __float2half_rn(acc);
@@ -125,9 +123,9 @@ SS_API int ss_skinny_gemm_f16(const void* x, int ldx, const void* W, void* y, in
                               int epilogue, const void* residual, int ldr, void* stream) {
   SS_REQUIRE(B >= 1 && B <= 8, "skinny GEMM handles 1..8 rows");
   SS_REQUIRE(K % 32 == 0 && ldx % 8 == 0, "K must be a multiple of 32, ldx of 8");
-  SS_REQUIRE(epilogue != EPI_SWIGLU || N % 16 == 0, "SwiGLU needs N % 16 == 0");
+  SS_REQUIRE(epilogue != EPI_SWIGLU || N % 8 == 0, "SwiGLU needs N % 8 == 0");
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = ceil_div(N, 16);
+  const int grid = ceil_div(N, SG_ROWS);
   const __half *xp = (const __half*)x, *Wp = (const __half*)W, *rp = (const __half*)residual;
   __half* yp = (__half*)y;
   switch (epilogue) {
