@@ -140,21 +140,29 @@ __global__ void groupnorm_partial_kernel(const T* __restrict__ x, float* __restr
   }
 }
 
+// one warp per (image, group): lanes stride over the per-CTA partials, then a fixed-order butterfly (deterministic)
 __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int chunks,
                                           int groups, float inv_cnt, float eps, int total) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g)
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (n, g)
+  const int lane = threadIdx.x & 31;
   if (i >= total) return;
   const int n = i / groups, g = i % groups;
   float s = 0.f, q = 0.f;
-  for (int c = 0; c < chunks; ++c) {
+  for (int c = lane; c < chunks; c += 32) {
     const float* p = partial + (((size_t)n * chunks + c) * groups + g) * 2;
     s += p[0];
     q += p[1];
   }
-  const float mean = s * inv_cnt;
-  const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
-  stats[2 * i] = mean;
-  stats[2 * i + 1] = rsqrtf(var + eps);
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    const float mean = s * inv_cnt;
+    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+    stats[2 * i] = mean;
+    stats[2 * i + 1] = rsqrtf(var + eps);
+  }
 }
 
 template <typename T>
@@ -226,8 +234,8 @@ SS_API int ss_groupnorm_nhwc(int dtype, const void* x, void* y, const void* gamm
     groupnorm_partial_kernel<__nv_bfloat16><<<dim3(chunks, N), block, smem, s>>>((const __nv_bfloat16*)x, partial, HW,
                                                                                C, groups, pix_per_cta);
   SS_LAUNCH_CHECK();
-  groupnorm_finalize_kernel<<<ceil_div(N * groups, 128), 128, 0, s>>>(partial, stats, chunks, groups, inv_cnt, eps,
-                                                                     N * groups);
+  groupnorm_finalize_kernel<<<ceil_div(N * groups, 4), 128, 0, s>>>(partial, stats, chunks, groups, inv_cnt, eps,
+                                                                   N * groups);
   SS_LAUNCH_CHECK();
   if (dtype == SS_F16)
     groupnorm_apply_kernel<__half><<<ew_grid(total_vecs), EW_THREADS, 0, s>>>(

@@ -1,13 +1,14 @@
 // Fused attention on the 5th-gen tensor cores (tcgen05 + TMEM), fp16, head_dim 64 / 128.
 //   S = Q K^T     tcgen05.mma  M=128 (queries) x N=128 (keys) x K=D, operands from TMA-staged shared memory,
 //                 accumulator in TMEM (two S buffers: the MMA of tile j+1 overlaps the softmax of tile j)
-//   softmax       128 threads, ONE QUERY ROW PER THREAD (tcgen05.ld 32x32b gives each lane a full row slice, so
-//                 row max / row sum need no shuffles); exp2 with the scale folded in; P written as fp16 into
-//                 128B-swizzled shared memory
+//   softmax       256 threads: a query row is shared by a PAIR of threads (warps w and w+4 see the same TMEM lanes),
+//                 each owning 64 of the tile's 128 keys and half of the output dims, so a thread reads its S slice
+//                 once (tcgen05.ld 32x32b), exchanges the row max with its partner through shared memory, and
+//                 writes its fp16 P slice (= one 128B-swizzled 64-key atom) for the next MMA
 //   PV = P V      tcgen05.mma  M=128 x N=D x K=128 with V as an MN-major B operand straight from the [key][d]
 //                 layout TMA delivers; the per-tile product is read back and folded into the fp32 running output
 //                 held in registers (O = O * corr + PV), so no TMEM rescale pass is needed
-// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = softmax + output (one row per thread).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = softmax + output.
 // Same mask semantics as fmha.cu: causal diagonal anchored bottom-right (xformers LowerTriangularFromBottomRightMask,
 // modeling_llama_xformer.py:289-295), keys >= Lk masked.  Operands are row-matrix views (token rows, heads side by
 // side in a row) so fused QKV buffers are consumed in place.
@@ -17,7 +18,7 @@
 
 namespace {
 
-constexpr int FT_BM = 128, FT_BN = 128, FT_THREADS = 192;
+constexpr int FT_BM = 128, FT_BN = 128, FT_THREADS = 320;  // TMA + MMA warps, 8 softmax warps
 
 struct FtParams {
   __half* o;
@@ -37,7 +38,7 @@ struct FtSmem {
   static constexpr int KV_BYTES = (D / 64) * ATOM;  // K tile or V tile
   static constexpr int P_BYTES = 2 * ATOM;
   static constexpr int STAGES = 2;
-  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + 1024 + 256;
+  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + 1024 + 256 + 2048 /*row-max exchange*/;
 };
 
 // MN-major B operand (V as [key][d] rows of 128 bytes, 128B swizzle): SBO = 8 key rows * 128 B, LBO = distance between
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
   uint64_t* p_full = bars + 9;      // 1
   uint64_t* pv_full = bars + 10;    // 1
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  float* xchg = reinterpret_cast<float*>(bars + 16);  // [2 halves][128 rows] row-max exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * FT_BM;
@@ -94,9 +96,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
         tc::mbar_init(&kv_full[i], 1);
         tc::mbar_init(&kv_empty[i], 1);
         tc::mbar_init(&s_full[i], 1);
-        tc::mbar_init(&s_empty[i], 4);
+        tc::mbar_init(&s_empty[i], 8);
       }
-      tc::mbar_init(p_full, 4);
+      tc::mbar_init(p_full, 8);
       tc::mbar_init(pv_full, 1);
       tc::fence_barrier_init();
     }
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
 
   if (ntiles == 0) {
     // nothing visible (only possible for degenerate causal shapes): write zeros
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
       const int r = (warp & 3) * 32 + lane;
       if (m0 + r < Lq) {
         __half* orow = p.o + b * p.o_sb + (long long)(m0 + r) * p.o_sl + h * p.o_sh;
@@ -180,21 +182,23 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       }
     }
   } else {
-    // ================= softmax + output: one query row per thread =================
-    const int q = warp & 3;
+    // ================= softmax + output: a pair of threads per query row =================
+    const int q = warp & 3;            // TMEM lane quarter
+    const int half = (warp - 2) >> 2;  // which 64 keys of the tile / which half of the output dims
     const int r = q * 32 + lane;
     const int qrow = m0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float o_acc[D];
+    constexpr int DH = D / 2;
+    float o_acc[DH];
 #pragma unroll
-    for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
+    for (int i = 0; i < DH; ++i) o_acc[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
 
     auto add_pv = [&]() {
 #pragma unroll
-      for (int c = 0; c < D; c += 32) {
+      for (int c = 0; c < DH; c += 32) {
         uint32_t raw[32];
-        tc::tmem_ld_32x32(tmem_PV + lane_off + c, raw);
+        tc::tmem_ld_32x32(tmem_PV + lane_off + half * DH + c, raw);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) o_acc[c + i] += __uint_as_float(raw[i]);
@@ -202,83 +206,86 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
     };
 
     for (int j = 0; j < ntiles; ++j) {
-      const uint32_t tS = tmem_S0 + (j & 1) * 128 + lane_off;
-      const int key0 = j * FT_BN;
-      const bool need_mask = (key0 + FT_BN > Lk) || (p.causal && (key0 + FT_BN - 1 > m0 + q * 32 + shift));
+      const uint32_t tS = tmem_S0 + (j & 1) * 128 + lane_off + half * 64;
+      const int key0 = j * FT_BN + half * 64;
+      const bool need_mask = (key0 + 64 > Lk) || (p.causal && (key0 + 63 > m0 + q * 32 + shift));
       const int key_lim = p.causal ? min(Lk - 1, qrow + shift) : (Lk - 1);  // last visible key for this row
       tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc::fence_after_sync();
-      // pass 1: row maximum
-      float mx = m_run;
-#pragma unroll 1
-      for (int c = 0; c < FT_BN; c += 32) {
+      // my 64 scores, read once
+      float sv[64];
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
         uint32_t raw[32];
         tc::tmem_ld_32x32(tS + c, raw);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float sv = __uint_as_float(raw[i]);
-          if (need_mask && key0 + c + i > key_lim) sv = -INFINITY;
-          mx = fmaxf(mx, sv);
-        }
+        for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(raw[i]);
       }
+      // S_j is in registers: the MMA warp may overwrite this buffer with S_{j+2}
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s_empty[j & 1]);
+      float mx = -INFINITY;
+      if (need_mask) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          if (key0 + i > key_lim) sv[i] = -INFINITY;
+          mx = fmaxf(mx, sv[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, sv[i]);
+      }
+      // exchange the half-row maxima with the partner thread (same row, other 64 keys)
+      xchg[half * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(fmaxf(mx, xchg[(half ^ 1) * 128 + r]), m_run);
       const float msc = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
       const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2 - msc);
-      // fold in the previous tile's P V (it was computed relative to the previous maximum), then rescale
+      // fold in the previous tile's P V (computed relative to the previous maximum), then rescale
       if (j > 0) {
         tc::mbar_wait(pv_full, (j - 1) & 1);
         tc::fence_after_sync();
         add_pv();
       }
 #pragma unroll
-      for (int i = 0; i < D; ++i) o_acc[i] *= corr;
+      for (int i = 0; i < DH; ++i) o_acc[i] *= corr;
       l_run *= corr;
       m_run = mx;
-      // pass 2: probabilities -> shared memory (fp16, 128B-swizzled atoms of 64 keys)
+      // probabilities of my 64 keys -> P atom `half` (fp16, 128B-swizzled rows of 128 bytes)
       float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < FT_BN; c += 32) {
-        uint32_t raw[32];
-        tc::tmem_ld_32x32(tS + c, raw);
-        tc::tmem_ld_wait();
-        if (c + 32 >= FT_BN) {  // last read of S_j: the MMA warp may overwrite this buffer with S_{j+2}
-          tc::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&s_empty[j & 1]);
-        }
-        uint32_t packed[16];
+      uint8_t* prow = sP + half * S::ATOM + r * 128;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a = __uint_as_float(raw[i]), bb = __uint_as_float(raw[i + 1]);
-          if (need_mask && key0 + c + i > key_lim) a = -INFINITY;
-          if (need_mask && key0 + c + i + 1 > key_lim) bb = -INFINITY;
-          const float pa = exp2f(a * p.scale_log2 - msc), pb = exp2f(bb * p.scale_log2 - msc);
+      for (int g8 = 0; g8 < 8; ++g8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float pa = exp2f(sv[g8 * 8 + 2 * i] * p.scale_log2 - msc);
+          const float pb = exp2f(sv[g8 * 8 + 2 * i + 1] * p.scale_log2 - msc);
           lsum += pa + pb;
           __half2 hh = __floats2half2_rn(pa, pb);
-          packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          pk[i] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        uint8_t* atom = sP + (c >> 6) * S::ATOM + r * 128;
-#pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
-          const int jj = ((c & 63) >> 3) + g4;  // 16-byte piece within the 128-byte row
-          *reinterpret_cast<uint4*>(atom + ((jj ^ (r & 7)) << 4)) =
-              make_uint4(packed[4 * g4], packed[4 * g4 + 1], packed[4 * g4 + 2], packed[4 * g4 + 3]);
-        }
+        *reinterpret_cast<uint4*>(prow + ((g8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       l_run += lsum;
       tc::fence_proxy_async();
-      __syncwarp();
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // partner has read my max before I overwrite it next tile
       if (lane == 0) tc::mbar_arrive(p_full);
     }
-    // last tile's P V
+    // last tile's P V, then combine the two halves' row sums
     tc::mbar_wait(pv_full, (ntiles - 1) & 1);
     tc::fence_after_sync();
     add_pv();
+    xchg[half * 128 + r] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    const float l_tot = l_run + xchg[(half ^ 1) * 128 + r];
     if (qrow < Lq) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __half* orow = p.o + b * p.o_sb + (long long)qrow * p.o_sl + h * p.o_sh;
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      __half* orow = p.o + b * p.o_sb + (long long)qrow * p.o_sl + h * p.o_sh + half * DH;
 #pragma unroll
-      for (int c = 0; c < D; c += 8) {
+      for (int c = 0; c < DH; c += 8) {
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = o_acc[c + i] * inv;

@@ -20,7 +20,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 bytes = one swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 192;          // v1 kernel: 2 + 4 warps
+constexpr int GEMM_PERSIST_THREADS = 320;  // v2 kernel: TMA, MMA + two epilogue groups of 4 warps
 
 struct GemmParams {
   void* out;
@@ -256,18 +257,19 @@ struct PersistLayout {
   static constexpr int B_BYTES = BN * BK * 2;   // per atom
   static constexpr int STAGE_BYTES = KATOMS * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
-  static constexpr int STAGING_BYTES = 4 /*warps*/ * 2 /*bufs*/ * 32 * 128;
+  static constexpr int STAGING_BYTES = 8 /*epilogue warps*/ * 32 * 128;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <typename T, int BN, bool CONV>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB,
                                                                          const __grid_constant__ CUtensorMap tmC,
                                                                          const GemmParams p, int n_tiles_n,
                                                                          int total_tiles) {
   using L = PersistLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + L::STAGES * L::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + L::STAGING_BYTES);
@@ -329,6 +331,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
+      pdl_wait();  // A (and everything the epilogue reads) is produced by earlier kernels in the stream
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n0, m0, img, y0, x0;
@@ -387,12 +390,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
-    const int q = warp & 3;  // TMEM lane quarter
+    // ================= epilogue: two groups of 4 warps (warps 2..5 and 6..9) =================
+    // group g drains TMEM accumulator g, i.e. every other tile of this CTA, so two epilogues are in flight
+    // while the MMA warp works on the next tile.
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;   // 0 or 1
     const int r = q * 32 + lane;
-    uint8_t* my_staging = staging + q * (2 * 32 * 128);
-    uint32_t lt = 0, sbuf = 0;
+    uint8_t* stg = staging + ((grp * 4 + q) * (32 * 128));
+    pdl_wait();  // residual / bias2 come from earlier kernels; our stores must not overtake their readers
+    uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      if ((int)(lt & 1) != grp) continue;
       int n0, m0, img, y0, x0;
       tile_coords(tile, n0, m0, img, y0, x0);
       const uint32_t buf = lt & 1, use = lt >> 1;
@@ -400,21 +408,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
       tc::fence_after_sync();
       const long long m = (long long)m0 + r;
       const bool row_ok = m < (long long)p.M;
-      const T* res_row = p.residual ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
-      const T* b2_row =
-          p.bias2 ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2 : nullptr;
+      const T* res_row = (p.residual && row_ok) ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
+      const T* b2_row = (p.bias2 && row_ok)
+                            ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2
+                            : nullptr;
+      const T* bias = reinterpret_cast<const T*>(p.bias);
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 
       // one staging fill = 64 output columns (128 bytes per row): 64 accumulator columns, or 128 with a GLU
       const int acc_per_fill = p.glu ? 128 : 64;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += acc_per_fill) {
-        uint8_t* stg = my_staging + sbuf * (32 * 128);
-        if (lane == 0) tc::tma_store_wait_read<1>();  // the store that last used this buffer has read it
+        if (lane == 0) tc::tma_store_wait_read<0>();  // the previous store from this buffer has been read out
         __syncwarp();
 #pragma unroll 1
         for (int cc = 0; cc < acc_per_fill; cc += 32) {
           const int c = c0 + cc;
+          const int col0 = n0 + c;
+          // issue every global load of this chunk up front (independent requests, one exposed latency)
+          vec8 vb[4], vr[4], vb2[4];
+#pragma unroll
+          for (int gI = 0; gI < 4; ++gI) {
+            const int col = col0 + gI * 8;
+            const bool col_ok = col < p.N;
+            vb[gI] = (bias && col_ok) ? ld_cached16(bias + col) : vec8{0u, 0u, 0u, 0u};
+            vr[gI] = (res_row && col_ok) ? ld_cached16(res_row + col) : vec8{0u, 0u, 0u, 0u};
+            vb2[gI] = (b2_row && col_ok) ? ld_cached16(b2_row + col) : vec8{0u, 0u, 0u, 0u};
+          }
           uint32_t raw[32];
           tc::tmem_ld_32x32(taddr + (uint32_t)c, raw);
           tc::tmem_ld_wait();
@@ -423,26 +443,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[buf]);
           }
-          const int col0 = n0 + c;
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
 #pragma unroll
           for (int gI = 0; gI < 4; ++gI) {
-            const int col = col0 + gI * 8;
             float* vv = v + gI * 8;
-            const bool col_ok = col < p.N;
-            if (p.bias && col_ok) {
-              float bf[8];
-              unpack8<T>(ld_cached16(reinterpret_cast<const T*>(p.bias) + col), bf);
+            float bf[8];
+            unpack8<T>(vb[gI], bf);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] += bf[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i]));
-            if (b2_row && col_ok && row_ok) {
-              float bf[8];
-              unpack8<T>(ld_cached16(b2_row + col), bf);
+            for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
+            if (p.bias2) {
+              unpack8<T>(vb2[gI], bf);
 #pragma unroll
               for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
             }
@@ -451,11 +463,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(act_apply<T>(vv[i], p.act)));
               }
-              if (res_row && col_ok && row_ok) {
-                float rf[8];
-                unpack8<T>(ld_cached16(res_row + col), rf);
+              if (p.residual) {
+                unpack8<T>(vr[gI], bf);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] += rf[i];
+                for (int i = 0; i < 8; ++i) vv[i] += bf[i];
               }
               // 16-byte piece j of this row inside the 128-byte staging row, 128B-swizzled like the TMA expects
               const int j = (cc >> 3) + gI;
@@ -469,11 +480,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
                 if (p.glu == 1)
                   o = a * ss_num<T>::to_f(ss_num<T>::from_f(gelu_erf(b)));
                 else
-                  o = ss_num<T>::to_f(ss_num<T>::from_f(a / (1.f + expf(-a)))) * b;
+                  o = ss_num<T>::to_f(ss_num<T>::from_f(a / (1.f + __expf(-a)))) * b;
                 o4[i] = ss_num<T>::from_f(o);
               }
               // 8 accumulator columns -> 4 outputs = 8 bytes; output column within the fill = (cc + gI*8) / 2
-              const int ocol = (cc + gI * 8) >> 1;          // 0..63
+              const int ocol = (cc + gI * 8) >> 1;               // 0..63
               const int j = ocol >> 3, within = (ocol & 7) * 2;  // 16-byte piece, byte offset inside it
               *reinterpret_cast<uint2*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4) + within) =
                   *reinterpret_cast<const uint2*>(o4);
@@ -489,7 +500,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
             tc::tma_store_2d(&tmC, stg, out_col, m0 + q * 32);
           tc::tma_store_commit();
         }
-        sbuf ^= 1;
       }
     }
     if (lane == 0) tc::tma_store_wait_all<0>();
@@ -654,8 +664,8 @@ int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     attr_set = true;
   }
   const int grid = (int)(total_tiles < sm_count() ? total_tiles : sm_count());
-  gemm_tc_persist_kernel<T, BN, CONV><<<grid, GEMM_THREADS, L::TOTAL, s>>>(ta, tb, tcm, p, n_tiles_n, (int)total_tiles);
-  SS_LAUNCH_CHECK();
+  SS_CUDA(ss::launch_pdl(gemm_tc_persist_kernel<T, BN, CONV>, dim3(grid), dim3(GEMM_PERSIST_THREADS), (size_t)L::TOTAL, s,
+                         ta, tb, tcm, p, n_tiles_n, (int)total_tiles));
   return 0;
 }
 

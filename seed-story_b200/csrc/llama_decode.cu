@@ -163,7 +163,8 @@ __device__ __forceinline__ __half hadd_t(__half a, __half b) {  // torch's half 
   return __float2half_rn(__half2float(a) + __half2float(b));
 }
 
-__global__ void __launch_bounds__(256) rope_append_kernel(const __half* __restrict__ qkv, int ld_qkv,
+// grid (ntok, H): one CTA per (token, head), D/2 threads: thread d owns the pair (d, d + D/2)
+__global__ void __launch_bounds__(128) rope_append_kernel(const __half* __restrict__ qkv, int ld_qkv,
                                                           __half* __restrict__ q_out, __half* __restrict__ kcache,
                                                           __half* __restrict__ vcache, const int* __restrict__ tok_seq,
                                                           const int* __restrict__ tok_pos,
@@ -173,43 +174,37 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const __half* __restri
                                                           const __half* __restrict__ sin_t, int H, int D) {
   pdl_trigger();
   pdl_wait();
-  const int tok = blockIdx.x;
+  const int tok = blockIdx.x, h = blockIdx.y;
+  const int half_d = D >> 1;
+  const int d = threadIdx.x;
+  if (d >= half_d) return;
   const int seq = tok_seq[tok], pos = tok_pos[tok], slot = tok_slot[tok];
   const int page = page_table[(size_t)seq * max_pages + slot / KV_PAGE];
   const int in_page = slot % KV_PAGE;
-  const int half_d = D >> 1;
   const __half* row = qkv + (size_t)tok * ld_qkv;
   const __half* cr = cos_t + (size_t)pos * D;
   const __half* sr = sin_t + (size_t)pos * D;
   const int HD = H * D;
-  for (int i = threadIdx.x; i < H * half_d; i += blockDim.x) {
-    const int h = i / half_d, d = i % half_d;
-    const __half c0 = cr[d], c1 = cr[d + half_d], s0 = sr[d], s1 = sr[d + half_d];
-    const size_t dst = (((size_t)page * H + h) * KV_PAGE + in_page) * D;
-    {  // q
-      const __half x0 = row[h * D + d], x1 = row[h * D + d + half_d];
-      q_out[(size_t)tok * HD + h * D + d] = hadd_t(__hmul(x0, c0), __hmul(__hneg(x1), s0));
-      q_out[(size_t)tok * HD + h * D + d + half_d] = hadd_t(__hmul(x1, c1), __hmul(x0, s1));
-    }
-    {  // k
-      const __half x0 = row[HD + h * D + d], x1 = row[HD + h * D + d + half_d];
-      kcache[dst + d] = hadd_t(__hmul(x0, c0), __hmul(__hneg(x1), s0));
-      kcache[dst + d + half_d] = hadd_t(__hmul(x1, c1), __hmul(x0, s1));
-    }
-    {  // v (raw)
-      vcache[dst + d] = row[2 * HD + h * D + d];
-      vcache[dst + d + half_d] = row[2 * HD + h * D + d + half_d];
-    }
-  }
+  const __half c0 = cr[d], c1 = cr[d + half_d], s0 = sr[d], s1 = sr[d + half_d];
+  const size_t dst = (((size_t)page * H + h) * KV_PAGE + in_page) * D;
+  const __half q0 = row[h * D + d], q1 = row[h * D + d + half_d];
+  const __half k0 = row[HD + h * D + d], k1 = row[HD + h * D + d + half_d];
+  const __half v0 = row[2 * HD + h * D + d], v1 = row[2 * HD + h * D + d + half_d];
+  q_out[(size_t)tok * HD + h * D + d] = hadd_t(__hmul(q0, c0), __hmul(__hneg(q1), s0));
+  q_out[(size_t)tok * HD + h * D + d + half_d] = hadd_t(__hmul(q1, c1), __hmul(q0, s1));
+  kcache[dst + d] = hadd_t(__hmul(k0, c0), __hmul(__hneg(k1), s0));
+  kcache[dst + d + half_d] = hadd_t(__hmul(k1, c1), __hmul(k0, s1));
+  vcache[dst + d] = v0;
+  vcache[dst + d + half_d] = v1;
 }
 
 SS_API int ss_rope_kv_append_f16(const void* qkv, int ld_qkv, void* q_out, void* kcache, void* vcache,
                                  const int* tok_seq, const int* tok_pos, const int* tok_slot, int ntok,
                                  const int* page_table, int max_pages, const void* cos_table, const void* sin_table,
                                  int H, int D, void* stream) {
-  SS_REQUIRE(D % 2 == 0, "head dim must be even");
+  SS_REQUIRE(D % 2 == 0 && D <= 256, "head dim must be even and <= 256");
   if (ntok == 0) return 0;
-  SS_CUDA(ss::launch_pdl(rope_append_kernel, dim3(ntok), dim3(256), 0, (cudaStream_t)stream, (const __half*)qkv, ld_qkv,
+  SS_CUDA(ss::launch_pdl(rope_append_kernel, dim3(ntok, H), dim3(128), 0, (cudaStream_t)stream, (const __half*)qkv, ld_qkv,
                          (__half*)q_out, (__half*)kcache, (__half*)vcache, tok_seq, tok_pos, tok_slot, page_table,
                          max_pages, (const __half*)cos_table, (const __half*)sin_table, H, D));
   SS_LAUNCH_CHECK();
@@ -288,16 +283,35 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
     lsum += e;
   }
   const float l = block_sum(lsum, red);
-  // phase 3: O = sum_j p_j V[j]; thread d owns output dim d (coalesced 256-byte value rows)
-  float acc = 0.f;
-  const int d = threadIdx.x;
-#pragma unroll 8
-  for (int j = 0; j < cnt; ++j) {
+  // phase 3: O = sum_j p_j V[j].  16 lanes x 16 bytes cover one 256-byte value row, so a warp folds two tokens
+  // per iteration and the 4 warps stride over the chunk; partial rows are reduced through shared memory.
+  __shared__ float osm[AD_THREADS / 16][D + 4];
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int j = warp * 2 + sub; j < cnt; j += (AD_THREADS / 32) * 2) {
     const int tok = t0 + j;
     const int page = pt[tok / KV_PAGE];
-    acc += sc[j] * __half2float(vcache[(((size_t)page * H + h) * KV_PAGE + (tok % KV_PAGE)) * D + d]);
+    float vf[8];
+    unpack8<__half>(ld_cached16(vcache + (((size_t)page * H + h) * KV_PAGE + (tok % KV_PAGE)) * D + l16 * 8), vf);
+    const float pj = sc[j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += pj * vf[i];
   }
-  out[d] = acc;
+  {
+    float* orow = osm[warp * 2 + sub];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) orow[l16 * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;  // AD_THREADS == D
+    float o = 0.f;
+#pragma unroll
+    for (int r = 0; r < AD_THREADS / 16; ++r) o += osm[r][d];
+    out[d] = o;
+  }
   if (threadIdx.x == 0) {
     out[D] = m;
     out[D + 1] = l;

@@ -66,36 +66,37 @@ SS_API int ss_rmsnorm_f16(const void* x, int ldx, const void* weight, void* y, i
   return 0;
 }
 
-// LayerNorm over the last dim, fp32 statistics (two-pass on registers), affine, output rounded once.
-// Optional `add` row-broadcast term (positional embeddings added after the norm, e.g.
-// src/models/qwen_visual.py:146-148) with period add_rows: y = LN(x)*g+b (+ add[row % add_rows]).
-template <typename T, int VEC_PER_THREAD>
+// LayerNorm over the last dim: ONE WARP PER ROW (8 rows per CTA), the row lives in registers, fp32 statistics
+// (mean, then centred second moment), affine, output rounded once.  Optional second output
+// y2 = LN(x) + add[row % add_rows] (positional-embedding adds, e.g. src/models/qwen_visual.py:146-148).
+template <typename T, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ g,
-                                                        const T* __restrict__ b, T* __restrict__ y, int ldy, int K,
-                                                        float eps, const T* __restrict__ add, int add_rows,
+                                                        const T* __restrict__ b, T* __restrict__ y, int ldy, int rows,
+                                                        int K, float eps, const T* __restrict__ add, int add_rows,
                                                         T* __restrict__ y2, int ldy2) {
-  __shared__ float red[32];
-  const int row = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
   const T* xr = x + (size_t)row * ldx;
   const int nvec = K >> 3;
-  float f[VEC_PER_THREAD][8];
+  float f[MAXV][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < VEC_PER_THREAD; ++i) {
-    const int vi = threadIdx.x + i * 256;
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
     if (vi < nvec) {
-      vec8 v = ld_cached16(xr + vi * 8);
-      unpack8<T>(v, f[i]);
+      unpack8<T>(ld_cached16(xr + vi * 8), f[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += f[i][j];
     }
   }
-  const float mean = block_sum(s, red) / (float)K;
+  const float mean = warp_sum(s) / (float)K;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < VEC_PER_THREAD; ++i) {
-    const int vi = threadIdx.x + i * 256;
-    if (vi < nvec) {
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + i * 32 < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = f[i][j] - mean;
@@ -103,21 +104,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
       }
     }
   }
-  const float rstd = __frsqrt_rn(block_sum(q, red) / (float)K + eps);
+  const float rstd = __frsqrt_rn(warp_sum(q) / (float)K + eps);
 #pragma unroll
-  for (int i = 0; i < VEC_PER_THREAD; ++i) {
-    const int vi = threadIdx.x + i * 256;
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
     if (vi < nvec) {
       float gg[8], bb[8], o[8];
       unpack8<T>(ld_cached16(g + vi * 8), gg);
       if (b) unpack8<T>(ld_cached16(b + vi * 8), bb);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gg[j] + (b ? bb[j] : 0.f);
-      // round once to the storage type, as torch's LayerNorm kernel does
-      vec8 ov = pack8<T>(o);
+      const vec8 ov = pack8<T>(o);  // rounded once to the storage type, as torch's LayerNorm kernel does
       st16(y + (size_t)row * ldy + vi * 8, ov);
       if (add) {
-        // second output: LN(x) + add, both operands already in storage precision (an fp16 add)
         float a[8], r[8];
         unpack8<T>(ld_cached16(add + (size_t)(row % add_rows) * K + vi * 8), a);
         unpack8<T>(ov, r);
@@ -129,23 +128,35 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
   }
 }
 
+template <typename T>
+static int launch_layernorm(const void* x, int ldx, const void* gamma, const void* beta, void* y, int ldy, int rows, int K,
+                            float eps, const void* add, int add_rows, void* y2, int ldy2, cudaStream_t s) {
+  const dim3 grid((rows + 7) / 8), block(256);
+  const int nvec = K / 8;
+#define SS_LN_LAUNCH(MAXV)                                                                                          \
+  SS_CUDA(ss::launch_pdl(layernorm_kernel<T, MAXV>, grid, block, 0, s, (const T*)x, ldx, (const T*)gamma, (const T*)beta, \
+                         (T*)y, ldy, rows, K, eps, (const T*)add, add_rows, (T*)y2, ldy2))
+  if (nvec <= 4 * 32) {
+    SS_LN_LAUNCH(4);
+  } else if (nvec <= 8 * 32) {
+    SS_LN_LAUNCH(8);
+  } else {
+    SS_LN_LAUNCH(16);
+  }
+#undef SS_LN_LAUNCH
+  return 0;
+}
+
 SS_API int ss_layernorm(int dtype, const void* x, int ldx, const void* gamma, const void* beta, void* y, int ldy,
                         int rows, int K, float eps, const void* add, int add_rows, void* y2, int ldy2, void* stream) {
-  SS_REQUIRE(K % 8 == 0 && K <= 256 * 8 * 2, "K must be a multiple of 8 and <= 4096");
+  SS_REQUIRE(K % 8 == 0 && K <= 4096, "K must be a multiple of 8 and <= 4096");
   SS_REQUIRE(dtype == SS_F16 || dtype == SS_BF16, "dtype");
   SS_REQUIRE(add == nullptr || (y2 != nullptr && add_rows > 0), "add needs y2/add_rows");
   if (rows == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == SS_F16)
-    layernorm_kernel<__half, 2><<<rows, 256, 0, s>>>((const __half*)x, ldx, (const __half*)gamma, (const __half*)beta,
-                                                     (__half*)y, ldy, K, eps, (const __half*)add, add_rows,
-                                                     (__half*)y2, ldy2);
-  else
-    layernorm_kernel<__nv_bfloat16, 2><<<rows, 256, 0, s>>>(
-        (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (__nv_bfloat16*)y, ldy,
-        K, eps, (const __nv_bfloat16*)add, add_rows, (__nv_bfloat16*)y2, ldy2);
-  SS_LAUNCH_CHECK();
-  return 0;
+    return launch_layernorm<__half>(x, ldx, gamma, beta, y, ldy, rows, K, eps, add, add_rows, y2, ldy2, s);
+  return launch_layernorm<__nv_bfloat16>(x, ldx, gamma, beta, y, ldy, rows, K, eps, add, add_rows, y2, ldy2, s);
 }
 
 // F.normalize(x) with x [B, T, C]: L2 norm over dim=1 (the TOKEN axis — src/models_ipa/resampler.py:269),
