@@ -129,9 +129,13 @@ class StoryPipeline:
         return ForcedScheduleProcessor(sched)
 
     @torch.no_grad()
-    def run_story(self, image_tensor, caption_ids, n_turns, decode_images=True, return_images=False):
+    def run_story(self, image_tensor, caption_ids, n_turns, decode_images=True, return_images=False, overlap=True):
         """image_tensor [1,3,S,S] fp16 on the device (CLIP-normalised); caption_ids: list[int].
-        Returns list of per-turn dicts(generate_ids, image_uint8 | None)."""
+        Returns list of per-turn dicts(generate_ids, image_uint8 | None).
+
+        overlap=True issues the SDXL de-tokenizer of turn t on a side stream while the MLLM already decodes turn
+        t+1: the next turn only needs `img_gen_feat` (gen_george.py:224), the pixels are merely saved
+        (gen_george.py:210-222) — SURVEY.md §8f rank 1.  Results are identical to the sequential order."""
         from src.models_clm.generation import AutoImageTokenGenerationProcessor
         tk, dev = self.tokenizer, self.dev
         input_ids = [tk.bos_token_id] + list(caption_ids) + self.image_ids
@@ -139,6 +143,14 @@ class StoryPipeline:
         procs = [AutoImageTokenGenerationProcessor(tk, 64), self._schedule()]
         outs = []
         res = self.cfg["image"]
+        main = torch.cuda.current_stream()
+        if overlap and decode_images:
+            if not hasattr(self, "_side"):
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+            side.wait_stream(main)
+        else:
+            side = None
         for turn in range(n_turns):
             ids_t = torch.tensor([input_ids], dtype=torch.long, device=dev)
             boi = [i for i, t in enumerate(input_ids) if t == tk.boi]
@@ -153,9 +165,18 @@ class StoryPipeline:
             assert out["has_img_output"], "forced schedule must produce an image run"
             img = None
             if decode_images:
-                imgs = self.adapter.generate(image_embeds=out["img_gen_feat"], num_inference_steps=self.steps,
-                                             height=res, width=res, output_type="pt",
-                                             input_image_size=self.cfg["vit"]["image_size"])
+                feat = out["img_gen_feat"]
+                if side is not None:
+                    side.wait_stream(main)       # img_gen_feat was produced on the main stream
+                    feat.record_stream(side)
+                    with torch.cuda.stream(side):
+                        imgs = self.adapter.generate(image_embeds=feat, num_inference_steps=self.steps, height=res,
+                                                     width=res, output_type="pt",
+                                                     input_image_size=self.cfg["vit"]["image_size"])
+                else:
+                    imgs = self.adapter.generate(image_embeds=feat, num_inference_steps=self.steps, height=res,
+                                                 width=res, output_type="pt",
+                                                 input_image_size=self.cfg["vit"]["image_size"])
                 img = imgs[0]
             gen = out["generate_ids"].tolist()
             outs.append(dict(generate_ids=gen, image=img if return_images else None))
@@ -166,4 +187,6 @@ class StoryPipeline:
                 first_eoi = input_ids.index(tk.eoi)
                 input_ids = [tk.bos_token_id] + input_ids[first_eoi + 1:]
                 image_embeds = image_embeds[1:]
+        if side is not None:
+            main.wait_stream(side)               # every image is complete before the caller touches the results
         return outs
