@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int FT_BM = 128, FT_BN = 128, FT_THREADS = 320;  // TMA + MMA warps, 8 softmax warps
+constexpr int FT_BM = 128, FT_BN = 64, FT_THREADS = 320;  // TMA + MMA warps, 8 softmax warps; 64-key tiles
 
 struct FtParams {
   __half* o;
@@ -33,16 +33,20 @@ struct FtParams {
 
 template <int D>
 struct FtSmem {
-  static constexpr int ATOM = 128 * 128;            // [128 rows][64 x 16-bit] = 16 KB
+  static constexpr int ATOM = 128 * 128;            // [128 rows][64 x 16-bit] = 16 KB (Q, P)
+  static constexpr int KATOM = FT_BN * 128;         // [64 keys][64 x 16-bit] = 8 KB (K, V)
   static constexpr int Q_BYTES = (D / 64) * ATOM;
-  static constexpr int KV_BYTES = (D / 64) * ATOM;  // K tile or V tile
-  static constexpr int P_BYTES = 2 * ATOM;
+  static constexpr int KV_BYTES = (D / 64) * KATOM;  // K tile or V tile
+  static constexpr int P_BYTES = ATOM;
   static constexpr int STAGES = 2;
-  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + 1024 + 256 + 2048 /*row-max exchange*/;
+  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + 1024 + 256 + 1024 /*row-max exchange*/;
+  // two CTAs per SM for D = 64 (64 KB + 192 TMEM columns each): one CTA's softmax overlaps the other's MMAs
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int MIN_CTAS = (D == 64) ? 2 : 1;
 };
 
 // MN-major B operand (V as [key][d] rows of 128 bytes, 128B swizzle): SBO = 8 key rows * 128 B, LBO = distance between
-// 64-wide d atoms (128 keys * 128 B)
+// 64-wide d atoms (64 keys * 128 B)
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
@@ -54,7 +58,7 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 }
 
 template <int D>
-__global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                 const __grid_constant__ CUtensorMap tmK,
                                                                 const __grid_constant__ CUtensorMap tmV,
                                                                 const FtParams p) {
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
   uint64_t* p_full = bars + 9;      // 1
   uint64_t* pv_full = bars + 10;    // 1
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
-  float* xchg = reinterpret_cast<float*>(bars + 16);  // [2 halves][128 rows] row-max exchange
+  float* xchg = reinterpret_cast<float*>(bars + 16);  // [2 halves][128 rows] row-max exchange (1 KB)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * FT_BM;
@@ -103,13 +107,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       tc::fence_barrier_init();
     }
     __syncwarp();
-    tc::tmem_alloc(tmem_ptr_smem, 512);
+    tc::tmem_alloc(tmem_ptr_smem, S::TMEM_COLS);
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S0 = tmem_base, tmem_PV = tmem_base + 256;
+  const uint32_t tmem_S0 = tmem_base, tmem_PV = tmem_base + 128;  // S: 2 x 64 columns, PV: D columns
 
   if (ntiles == 0) {
     // nothing visible (only possible for degenerate causal shapes): write zeros
@@ -138,8 +142,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
         tc::mbar_expect_tx(&kv_full[s], 2 * S::KV_BYTES);
 #pragma unroll
         for (int a = 0; a < D / 64; ++a) {
-          tc::tma_load_2d(sK + a * S::ATOM, &tmK, &kv_full[s], p.k_col0 + h * p.k_col_per_head + a * 64, krow0);
-          tc::tma_load_2d(sV + a * S::ATOM, &tmV, &kv_full[s], p.v_col0 + h * p.v_col_per_head + a * 64, krow0);
+          tc::tma_load_2d(sK + a * S::KATOM, &tmK, &kv_full[s], p.k_col0 + h * p.k_col_per_head + a * 64, krow0);
+          tc::tma_load_2d(sV + a * S::KATOM, &tmV, &kv_full[s], p.v_col0 + h * p.v_col_per_head + a * 64, krow0);
         }
       }
     }
@@ -157,9 +161,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
         const uint32_t aK = tc::smem_u32(sKV + s * 2 * S::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * S::ATOM + (kk & 3) * 32;
-          tc::mma_f16_ss(tmem_S0 + (j & 1) * 128, tc::make_desc_sw128(aQ + off), tc::make_desc_sw128(aK + off), idesc_qk,
-                         kk != 0);
+          const uint32_t offq = (kk >> 2) * S::ATOM + (kk & 3) * 32, offk = (kk >> 2) * S::KATOM + (kk & 3) * 32;
+          tc::mma_f16_ss(tmem_S0 + (j & 1) * FT_BN, tc::make_desc_sw128(aQ + offq), tc::make_desc_sw128(aK + offk),
+                         idesc_qk, kk != 0);
         }
         tc::mma_commit(&s_full[j & 1]);
       };
@@ -173,8 +177,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
         const uint32_t aV = tc::smem_u32(sKV + s * 2 * S::KV_BYTES + S::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < FT_BN / 16; ++kk) {
-          const uint64_t da = tc::make_desc_sw128(aP + (kk >> 2) * S::ATOM + (kk & 3) * 32);
-          const uint64_t db = make_desc_mn_sw128(aV + kk * 16 * 128, S::ATOM);
+          const uint64_t da = tc::make_desc_sw128(aP + kk * 32);
+          const uint64_t db = make_desc_mn_sw128(aV + kk * 16 * 128, S::KATOM);
           tc::mma_f16_ss(tmem_PV, da, db, idesc_pv, kk != 0);
         }
         tc::mma_commit(&kv_empty[s]);  // K_j / V_j no longer needed
@@ -206,21 +210,20 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
     };
 
     for (int j = 0; j < ntiles; ++j) {
-      const uint32_t tS = tmem_S0 + (j & 1) * 128 + lane_off + half * 64;
-      const int key0 = j * FT_BN + half * 64;
-      const bool need_mask = (key0 + 64 > Lk) || (p.causal && (key0 + 63 > m0 + q * 32 + shift));
+      const uint32_t tS = tmem_S0 + (j & 1) * FT_BN + lane_off + half * 32;
+      const int key0 = j * FT_BN + half * 32;
+      const bool need_mask = (key0 + 32 > Lk) || (p.causal && (key0 + 31 > m0 + q * 32 + shift));
       const int key_lim = p.causal ? min(Lk - 1, qrow + shift) : (Lk - 1);  // last visible key for this row
       tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc::fence_after_sync();
-      // my 64 scores, read once
-      float sv[64];
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
+      // my 32 scores, read once
+      float sv[32];
+      {
         uint32_t raw[32];
-        tc::tmem_ld_32x32(tS + c, raw);
+        tc::tmem_ld_32x32(tS, raw);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(raw[i]);
+        for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(raw[i]);
       }
       // S_j is in registers: the MMA warp may overwrite this buffer with S_{j+2}
       tc::fence_before_sync();
@@ -229,15 +232,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       float mx = -INFINITY;
       if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < 32; ++i) {
           if (key0 + i > key_lim) sv[i] = -INFINITY;
           mx = fmaxf(mx, sv[i]);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, sv[i]);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, sv[i]);
       }
-      // exchange the half-row maxima with the partner thread (same row, other 64 keys)
+      // exchange the half-row maxima with the partner thread (same row, other 32 keys)
       xchg[half * 128 + r] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       mx = fmaxf(fmaxf(mx, xchg[(half ^ 1) * 128 + r]), m_run);
@@ -253,11 +256,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       for (int i = 0; i < DH; ++i) o_acc[i] *= corr;
       l_run *= corr;
       m_run = mx;
-      // probabilities of my 64 keys -> P atom `half` (fp16, 128B-swizzled rows of 128 bytes)
+      // probabilities of my 32 keys -> my half of the 64-key P atom (fp16, 128B-swizzled rows of 128 bytes)
       float lsum = 0.f;
-      uint8_t* prow = sP + half * S::ATOM + r * 128;
+      uint8_t* prow = sP + r * 128;
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) {
+      for (int g8 = 0; g8 < 4; ++g8) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
           __half2 hh = __floats2half2_rn(pa, pb);
           pk[i] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        *reinterpret_cast<uint4*>(prow + ((g8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(prow + (((half * 4 + g8) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       l_run += lsum;
       tc::fence_proxy_async();
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
 // tensor-map helper (defined in gemm_tc.cu)
@@ -338,15 +341,15 @@ int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, 
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) return -1;
   if (o_sl % 8 != 0 || o_sh % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return -1;
   CUtensorMap tq, tk, tv;
-  auto mk = [&](CUtensorMap* tm, const void* ptr, long long sb, long long sl, int L) {
+  auto mk = [&](CUtensorMap* tm, const void* ptr, long long sb, long long sl, int L, uint32_t box_rows) {
     const uint64_t rows = (uint64_t)(sb == 0 ? L : (long long)B * L);
     uint64_t dims[2] = {(uint64_t)sl, rows}, str[1] = {(uint64_t)sl * 2};
-    uint32_t box[2] = {64, 128};
+    uint32_t box[2] = {64, box_rows};
     return ss_internal_get_tmap(tm, ptr, SS_F16, 2, dims, str, box);
   };
-  if (int e = mk(&tq, q, q_sb, q_sl, Lq)) return e;
-  if (int e = mk(&tk, k, k_sb, k_sl, Lk)) return e;
-  if (int e = mk(&tv, v, v_sb, v_sl, Lk)) return e;
+  if (int e = mk(&tq, q, q_sb, q_sl, Lq, FT_BM)) return e;
+  if (int e = mk(&tk, k, k_sb, k_sl, Lk, FT_BN)) return e;
+  if (int e = mk(&tv, v, v_sb, v_sl, Lk, FT_BN)) return e;
   FtParams p;
   memset(&p, 0, sizeof(p));
   p.o = (__half*)out;
