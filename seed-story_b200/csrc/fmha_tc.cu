@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int FT_BM = 128, FT_BN = 64, FT_THREADS = 320;  // TMA + MMA warps, 8 softmax warps; 64-key tiles
+constexpr int FT_BM = 128, FT_BN = 128, FT_THREADS = 320;  // TMA + MMA warps, 8 softmax warps
 
 struct FtParams {
   __half* o;
@@ -33,20 +33,17 @@ struct FtParams {
 
 template <int D>
 struct FtSmem {
-  static constexpr int ATOM = 128 * 128;            // [128 rows][64 x 16-bit] = 16 KB (Q, P)
-  static constexpr int KATOM = FT_BN * 128;         // [64 keys][64 x 16-bit] = 8 KB (K, V)
+  static constexpr int ATOM = 128 * 128;            // [128 rows][64 x 16-bit] = 16 KB
   static constexpr int Q_BYTES = (D / 64) * ATOM;
-  static constexpr int KV_BYTES = (D / 64) * KATOM;  // K tile or V tile
-  static constexpr int P_BYTES = ATOM;
+  static constexpr int KV_BYTES = (D / 64) * ATOM;  // K tile or V tile
+  static constexpr int P_BYTES = 2 * ATOM;
   static constexpr int STAGES = 2;
-  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + 1024 + 256 + 1024 /*row-max exchange*/;
-  // two CTAs per SM for D = 64 (64 KB + 192 TMEM columns each): one CTA's softmax overlaps the other's MMAs
-  static constexpr int TMEM_COLS = 256;
-  static constexpr int MIN_CTAS = (D == 64) ? 2 : 1;
+  static constexpr int ONES_BYTES = 4096;           // [16][128] fp16 ones: B operand of the row-sum MMA
+  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + ONES_BYTES + 1024 + 256 + 2048 /*row-max exchange*/;
 };
 
 // MN-major B operand (V as [key][d] rows of 128 bytes, 128B swizzle): SBO = 8 key rows * 128 B, LBO = distance between
-// 64-wide d atoms (64 keys * 128 B)
+// 64-wide d atoms (128 keys * 128 B)
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
@@ -58,7 +55,7 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 }
 
 template <int D>
-__global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                 const __grid_constant__ CUtensorMap tmK,
                                                                 const __grid_constant__ CUtensorMap tmV,
                                                                 const FtParams p) {
@@ -68,7 +65,8 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + S::Q_BYTES;                       // stage s: K at s*2*KV, V right after
   uint8_t* sP = sKV + S::STAGES * 2 * S::KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + S::P_BYTES);
+  uint8_t* sOnes = sP + S::P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + S::ONES_BYTES);
   uint64_t* q_full = bars;          // 1
   uint64_t* kv_full = bars + 1;     // [2]
   uint64_t* kv_empty = bars + 3;    // [2]
@@ -77,7 +75,7 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
   uint64_t* p_full = bars + 9;      // 1
   uint64_t* pv_full = bars + 10;    // 1
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
-  float* xchg = reinterpret_cast<float*>(bars + 16);  // [2 halves][128 rows] row-max exchange (1 KB)
+  float* xchg = reinterpret_cast<float*>(bars + 16);  // [2 halves][128 rows] row-max exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * FT_BM;
@@ -88,6 +86,8 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
   if (p.causal) n_end = min(Lk, m0 + FT_BM + shift);
   const int ntiles = (n_end + FT_BN - 1) / FT_BN;
 
+  for (int i = threadIdx.x; i < S::ONES_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3C003C00u;
+  tc::fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmQ);
     tc::prefetch_tmap(&tmK);
@@ -107,13 +107,13 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
       tc::fence_barrier_init();
     }
     __syncwarp();
-    tc::tmem_alloc(tmem_ptr_smem, S::TMEM_COLS);
+    tc::tmem_alloc(tmem_ptr_smem, 512);
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S0 = tmem_base, tmem_PV = tmem_base + 128;  // S: 2 x 64 columns, PV: D columns
+  const uint32_t tmem_S0 = tmem_base, tmem_PV = tmem_base + 256, tmem_L = tmem_base + 256 + D;  // L: row sums of P
 
   if (ntiles == 0) {
     // nothing visible (only possible for degenerate causal shapes): write zeros
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
         tc::mbar_expect_tx(&kv_full[s], 2 * S::KV_BYTES);
 #pragma unroll
         for (int a = 0; a < D / 64; ++a) {
-          tc::tma_load_2d(sK + a * S::KATOM, &tmK, &kv_full[s], p.k_col0 + h * p.k_col_per_head + a * 64, krow0);
-          tc::tma_load_2d(sV + a * S::KATOM, &tmV, &kv_full[s], p.v_col0 + h * p.v_col_per_head + a * 64, krow0);
+          tc::tma_load_2d(sK + a * S::ATOM, &tmK, &kv_full[s], p.k_col0 + h * p.k_col_per_head + a * 64, krow0);
+          tc::tma_load_2d(sV + a * S::ATOM, &tmV, &kv_full[s], p.v_col0 + h * p.v_col_per_head + a * 64, krow0);
         }
       }
     }
@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
     if (lane == 0) {
       constexpr uint32_t idesc_qk = tc::make_idesc(0, FT_BM, FT_BN);               // A, B K-major
       constexpr uint32_t idesc_pv = tc::make_idesc(0, FT_BM, D) | (1u << 16);      // B (V) MN-major
-      const uint32_t aQ = tc::smem_u32(sQ), aP = tc::smem_u32(sP);
+      const uint32_t aQ = tc::smem_u32(sQ), aP = tc::smem_u32(sP), aOnes = tc::smem_u32(sOnes);
+      constexpr uint32_t idesc_l = tc::make_idesc(0, FT_BM, 16);
       auto issue_qk = [&](int j) {
         const int s = j & 1;
         tc::mbar_wait(&kv_full[s], (j >> 1) & 1);
@@ -161,9 +162,9 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
         const uint32_t aK = tc::smem_u32(sKV + s * 2 * S::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t offq = (kk >> 2) * S::ATOM + (kk & 3) * 32, offk = (kk >> 2) * S::KATOM + (kk & 3) * 32;
-          tc::mma_f16_ss(tmem_S0 + (j & 1) * FT_BN, tc::make_desc_sw128(aQ + offq), tc::make_desc_sw128(aK + offk),
-                         idesc_qk, kk != 0);
+          const uint32_t off = (kk >> 2) * S::ATOM + (kk & 3) * 32;
+          tc::mma_f16_ss(tmem_S0 + (j & 1) * 128, tc::make_desc_sw128(aQ + off), tc::make_desc_sw128(aK + off), idesc_qk,
+                         kk != 0);
         }
         tc::mma_commit(&s_full[j & 1]);
       };
@@ -177,9 +178,11 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
         const uint32_t aV = tc::smem_u32(sKV + s * 2 * S::KV_BYTES + S::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < FT_BN / 16; ++kk) {
-          const uint64_t da = tc::make_desc_sw128(aP + kk * 32);
-          const uint64_t db = make_desc_mn_sw128(aV + kk * 16 * 128, S::KATOM);
+          const uint64_t da = tc::make_desc_sw128(aP + (kk >> 2) * S::ATOM + (kk & 3) * 32);
+          const uint64_t db = make_desc_mn_sw128(aV + kk * 16 * 128, S::ATOM);
           tc::mma_f16_ss(tmem_PV, da, db, idesc_pv, kk != 0);
+          // row sums of P_j by the tensor core: P (128 x 16 keys) times a 16 x 16 block of ones
+          tc::mma_f16_ss(tmem_L, da, tc::make_desc_sw128(aOnes + (kk >> 2) * 2048 + (kk & 3) * 32), idesc_l, kk != 0);
         }
         tc::mma_commit(&kv_empty[s]);  // K_j / V_j no longer needed
         tc::mma_commit(pv_full);
@@ -207,23 +210,26 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
 #pragma unroll
         for (int i = 0; i < 32; ++i) o_acc[c + i] += __uint_as_float(raw[i]);
       }
+      l_run += __uint_as_float(tc::tmem_ld_32x1(tmem_L + lane_off));
+      tc::tmem_ld_wait();
     };
 
     for (int j = 0; j < ntiles; ++j) {
-      const uint32_t tS = tmem_S0 + (j & 1) * FT_BN + lane_off + half * 32;
-      const int key0 = j * FT_BN + half * 32;
-      const bool need_mask = (key0 + 32 > Lk) || (p.causal && (key0 + 31 > m0 + q * 32 + shift));
+      const uint32_t tS = tmem_S0 + (j & 1) * 128 + lane_off + half * 64;
+      const int key0 = j * FT_BN + half * 64;
+      const bool need_mask = (key0 + 64 > Lk) || (p.causal && (key0 + 63 > m0 + q * 32 + shift));
       const int key_lim = p.causal ? min(Lk - 1, qrow + shift) : (Lk - 1);  // last visible key for this row
       tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc::fence_after_sync();
-      // my 32 scores, read once
-      float sv[32];
-      {
+      // my 64 scores, read once
+      float sv[64];
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
         uint32_t raw[32];
-        tc::tmem_ld_32x32(tS, raw);
+        tc::tmem_ld_32x32(tS + c, raw);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(raw[i]);
+        for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(raw[i]);
       }
       // S_j is in registers: the MMA warp may overwrite this buffer with S_{j+2}
       tc::fence_before_sync();
@@ -232,15 +238,15 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
       float mx = -INFINITY;
       if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 64; ++i) {
           if (key0 + i > key_lim) sv[i] = -INFINITY;
           mx = fmaxf(mx, sv[i]);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, sv[i]);
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, sv[i]);
       }
-      // exchange the half-row maxima with the partner thread (same row, other 32 keys)
+      // exchange the half-row maxima with the partner thread (same row, other 64 keys)
       xchg[half * 128 + r] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       mx = fmaxf(fmaxf(mx, xchg[(half ^ 1) * 128 + r]), m_run);
@@ -252,38 +258,38 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
         tc::fence_after_sync();
         add_pv();
       }
+      if (!__all_sync(0xffffffffu, corr == 1.f)) {  // the running maximum usually settles after a few tiles
 #pragma unroll
-      for (int i = 0; i < DH; ++i) o_acc[i] *= corr;
-      l_run *= corr;
+        for (int i = 0; i < DH; ++i) o_acc[i] *= corr;
+        l_run *= corr;
+      }
       m_run = mx;
-      // probabilities of my 32 keys -> my half of the 64-key P atom (fp16, 128B-swizzled rows of 128 bytes)
-      float lsum = 0.f;
-      uint8_t* prow = sP + r * 128;
+      // probabilities of my 64 keys -> P atom `half` (fp16, 128B-swizzled rows of 128 bytes)
+      // exp2 on packed halves (MUFU.EX2.F16x2: two results per issue); P is needed in fp16 anyway and its row
+      // sums come back from the tensor core (tmem_L), so no per-element adds are spent here
+      uint8_t* prow = sP + half * S::ATOM + r * 128;
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {
+      for (int g8 = 0; g8 < 8; ++g8) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float pa = exp2f(sv[g8 * 8 + 2 * i] * p.scale_log2 - msc);
-          const float pb = exp2f(sv[g8 * 8 + 2 * i + 1] * p.scale_log2 - msc);
-          lsum += pa + pb;
-          __half2 hh = __floats2half2_rn(pa, pb);
-          pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+          const float xa = fmaf(sv[g8 * 8 + 2 * i], p.scale_log2, -msc);
+          const float xb = fmaf(sv[g8 * 8 + 2 * i + 1], p.scale_log2, -msc);
+          uint32_t xh;
+          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(xb), "f"(xa));  // {hi: xb, lo: xa}
+          asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i]) : "r"(xh));
         }
-        *reinterpret_cast<uint4*>(prow + (((half * 4 + g8) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(prow + ((g8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      l_run += lsum;
       tc::fence_proxy_async();
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // partner has read my max before I overwrite it next tile
       if (lane == 0) tc::mbar_arrive(p_full);
     }
-    // last tile's P V, then combine the two halves' row sums
+    // last tile's P V and row sums
     tc::mbar_wait(pv_full, (ntiles - 1) & 1);
     tc::fence_after_sync();
     add_pv();
-    xchg[half * 128 + r] = l_run;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    const float l_tot = l_run + xchg[(half ^ 1) * 128 + r];
+    const float l_tot = l_run;  // tmem_L already holds sums over all 128 keys of each tile
     if (qrow < Lq) {
       const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
       __half* orow = p.o + b * p.o_sb + (long long)qrow * p.o_sl + h * p.o_sh + half * DH;
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(FT_THREADS, FtSmem<D>::MIN_CTAS) fmha_tc_kerne
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, S::TMEM_COLS);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // tensor-map helper (defined in gemm_tc.cu)
@@ -341,15 +347,15 @@ int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, 
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) return -1;
   if (o_sl % 8 != 0 || o_sh % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return -1;
   CUtensorMap tq, tk, tv;
-  auto mk = [&](CUtensorMap* tm, const void* ptr, long long sb, long long sl, int L, uint32_t box_rows) {
+  auto mk = [&](CUtensorMap* tm, const void* ptr, long long sb, long long sl, int L) {
     const uint64_t rows = (uint64_t)(sb == 0 ? L : (long long)B * L);
     uint64_t dims[2] = {(uint64_t)sl, rows}, str[1] = {(uint64_t)sl * 2};
-    uint32_t box[2] = {64, box_rows};
+    uint32_t box[2] = {64, 128};
     return ss_internal_get_tmap(tm, ptr, SS_F16, 2, dims, str, box);
   };
-  if (int e = mk(&tq, q, q_sb, q_sl, Lq, FT_BM)) return e;
-  if (int e = mk(&tk, k, k_sb, k_sl, Lk, FT_BN)) return e;
-  if (int e = mk(&tv, v, v_sb, v_sl, Lk, FT_BN)) return e;
+  if (int e = mk(&tq, q, q_sb, q_sl, Lq)) return e;
+  if (int e = mk(&tk, k, k_sb, k_sl, Lk)) return e;
+  if (int e = mk(&tv, v, v_sb, v_sl, Lk)) return e;
   FtParams p;
   memset(&p, 0, sizeof(p));
   p.o = (__half*)out;

@@ -398,9 +398,14 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
     const int r = q * 32 + lane;
     uint8_t* stg = staging + ((grp * 4 + q) * (32 * 128));
     pdl_wait();  // residual / bias2 come from earlier kernels; our stores must not overtake their readers
+    // one-tile CTAs (small problems): nothing to overlap with, so both groups split that tile's columns instead
+    const int acc_per_fill_k = p.glu ? 128 : 64;
+    const bool split_cols = (total_tiles <= (int)gridDim.x) && (BN / 2 >= acc_per_fill_k);
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      if ((int)(lt & 1) != grp) continue;
+      if (!split_cols && (int)(lt & 1) != grp) continue;
+      const int c_begin = split_cols ? grp * (BN / 2) : 0;
+      const int c_end = split_cols ? (grp + 1) * (BN / 2) : BN;
       int n0, m0, img, y0, x0;
       tile_coords(tile, n0, m0, img, y0, x0);
       const uint32_t buf = lt & 1, use = lt >> 1;
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
       // one staging fill = 64 output columns (128 bytes per row): 64 accumulator columns, or 128 with a GLU
       const int acc_per_fill = p.glu ? 128 : 64;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += acc_per_fill) {
+      for (int c0 = c_begin; c0 < c_end; c0 += acc_per_fill) {
         if (lane == 0) tc::tma_store_wait_read<0>();  // the previous store from this buffer has been read out
         __syncwarp();
 #pragma unroll 1
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
           uint32_t raw[32];
           tc::tmem_ld_32x32(taddr + (uint32_t)c, raw);
           tc::tmem_ld_wait();
-          if (c + 32 >= BN) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
+          if (c + 32 >= c_end) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[buf]);

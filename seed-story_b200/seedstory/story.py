@@ -129,11 +129,11 @@ class StoryPipeline:
         return ForcedScheduleProcessor(sched)
 
     @torch.no_grad()
-    def run_story(self, image_tensor, caption_ids, n_turns, decode_images=True, return_images=False, overlap=True):
+    def run_story(self, image_tensor, caption_ids, n_turns, decode_images=True, return_images=False, overlap=False):
         """image_tensor [1,3,S,S] fp16 on the device (CLIP-normalised); caption_ids: list[int].
         Returns list of per-turn dicts(generate_ids, image_uint8 | None).
 
-        overlap=True issues the SDXL de-tokenizer of turn t on a side stream while the MLLM already decodes turn
+        overlap=True (off by default: measured neutral on one B200, both phases already fill the GPU) issues the SDXL de-tokenizer of turn t on a side stream while the MLLM already decodes turn
         t+1: the next turn only needs `img_gen_feat` (gen_george.py:224), the pixels are merely saved
         (gen_george.py:210-222) — SURVEY.md §8f rank 1.  Results are identical to the sequential order."""
         from src.models_clm.generation import AutoImageTokenGenerationProcessor

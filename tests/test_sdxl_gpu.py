@@ -96,6 +96,6 @@ def test_story_pipeline_tiny_end_to_end(cuda_dev):
     assert [o["generate_ids"] for o in outs] == [o["generate_ids"] for o in outs2]
     assert all(torch.equal(a["image"], b["image"]) for a, b in zip(outs, outs2))
     # the side-stream overlap of SDXL(t) with the MLLM of turn t+1 must not change any result
-    outs3 = pipe.run_story(img, cap, n_turns=3, return_images=True, overlap=False)
+    outs3 = pipe.run_story(img, cap, n_turns=3, return_images=True, overlap=True)
     assert [o["generate_ids"] for o in outs] == [o["generate_ids"] for o in outs3]
     assert all(torch.equal(a["image"], b["image"]) for a, b in zip(outs, outs3))
