@@ -515,6 +515,269 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
   if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * BN);
 }
 
+
+// =============================================================================================
+// v3: CTA-pair kernel (cta_group::2).  A cluster of two CTAs (one TPC) owns a 256 x 256 output tile: each CTA
+// stages ITS 128 rows of A and ITS 128 rows (half) of the B tile, the leader CTA issues tcgen05.mma with M = 256
+// that reads both CTAs' shared memory, and each CTA's TMEM receives its own 128 accumulator rows.  Per CTA the
+// shared-memory traffic per MMA drops from (128 + 256) to (128 + 128) operand rows, which is what lets the
+// tensor pipe run past the single-CTA ceiling; stages shrink to 32 KB, so the ring is 6 deep.
+// Barrier protocol: both producers signal the LEADER's full barrier (TMA .cta_group::2 + remote arrive);
+// tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs; both epilogues arrive on the
+// leader's "accumulator drained" barrier.
+// =============================================================================================
+struct PairLayout {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = BM * BK * 2;        // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB: this CTA's half of the N tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int STAGING_BYTES = 8 * 32 * 128;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+};
+
+template <typename T, bool CONV>
+__global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                      const __grid_constant__ CUtensorMap tmB,
+                                                                      const __grid_constant__ CUtensorMap tmC,
+                                                                      const GemmParams p, int n_tiles_n,
+                                                                      int total_tiles) {
+  using L = PairLayout;
+  constexpr int BN = L::BN;
+  extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + L::STAGES * L::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + L::STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + L::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + L::STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();  // 0 = leader
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int kchunks = CONV ? (p.Cin / BK) : ((p.K + BK - 1) / BK);
+  const int num_kb = CONV ? 9 * kchunks : kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    tc::prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < L::STAGES; ++s) {
+      tc::mbar_init(&full_bar[s], 2);   // leader's copy is the one used: both CTAs' producers arrive on it
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&tmem_full_bar[b], 1);
+      tc::mbar_init(&tmem_empty_bar[b], 8);  // 4 epilogue warps of the owning group in EACH CTA (leader's copy)
+    }
+    tc::fence_barrier_init();
+  }
+  tc::cluster_sync();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  if (warp == 1) tc::tmem_alloc_2sm(tmem_ptr_smem, 2 * BN);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // pair tile -> this CTA's sub-tile coordinates
+  auto tile_coords = [&](int tile, int& n0, int& m0, int& img, int& y0, int& x0) {
+    const int tn = tile % n_tiles_n;
+    int st = (tile / n_tiles_n) * 2 + (int)rank;  // 128-row sub-tile index of this CTA
+    n0 = tn * BN;
+    if (CONV) {
+      const int tx = st % p.tiles_x;
+      st /= p.tiles_x;
+      const int ty = st % p.tiles_y;
+      img = st / p.tiles_y;
+      y0 = ty * p.bh;
+      x0 = tx * p.bw;
+      m0 = (img * p.H + y0) * p.W + x0;
+    } else {
+      m0 = st * BM;
+      img = y0 = x0 = 0;
+    }
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      pdl_wait();
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        int n0, m0, img, y0, x0;
+        tile_coords(tile, n0, m0, img, y0, x0);
+        const int nb0 = n0 + (int)rank * (BN / 2);  // my half of the B tile
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % L::STAGES;
+          const uint32_t ph = (it / L::STAGES) & 1;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (CONV) {
+            const int tap = kb / kchunks, c0 = (kb % kchunks) * BK;
+            const int ky = tap / 3, kx = tap % 3;
+            tc::tma_load_4d_2sm(sa, &tmA, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, img);
+            tc::tma_load_2d_2sm(sb, &tmB, &full_bar[s], tap * p.Cin + c0, nb0);
+          } else {
+            tc::tma_load_2d_2sm(sa, &tmA, &full_bar[s], kb * BK, m0);
+            tc::tma_load_2d_2sm(sb, &tmB, &full_bar[s], kb * BK, nb0);
+          }
+          if (rank == 0)
+            tc::mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);  // bytes of both CTAs land on the leader's barrier
+          else
+            tc::mbar_arrive_remote(&full_bar[s], 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(sizeof(T) == 2 && !std::is_same<T, __half>::value, 2 * BM, BN);
+      uint32_t it = 0, lt = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++lt) {
+        const uint32_t buf = lt & 1, use = lt >> 1;
+        tc::mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);
+        tc::fence_after_sync();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % L::STAGES;
+          const uint32_t ph = (it / L::STAGES) & 1;
+          tc::mbar_wait(&full_bar[s], ph);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t da = tc::make_desc_sw128(sa);
+          const uint64_t db = tc::make_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc::mma_f16_ss_2sm(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          tc::mma_commit_2sm(&empty_bar[s]);
+        }
+        tc::mma_commit_2sm(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ================= epilogue (both CTAs): two groups of 4 warps, each CTA drains its own 128 rows =================
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    uint8_t* stg = staging + ((grp * 4 + q) * (32 * 128));
+    pdl_wait();
+    const int acc_per_fill_k = p.glu ? 128 : 64;
+    const bool split_cols = (total_tiles <= num_clusters) && (BN / 2 >= acc_per_fill_k);
+    uint32_t lt = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++lt) {
+      if (!split_cols && (int)(lt & 1) != grp) continue;
+      const int c_begin = split_cols ? grp * (BN / 2) : 0;
+      const int c_end = split_cols ? (grp + 1) * (BN / 2) : BN;
+      int n0, m0, img, y0, x0;
+      tile_coords(tile, n0, m0, img, y0, x0);
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      tc::mbar_wait(&tmem_full_bar[buf], use & 1);
+      tc::fence_after_sync();
+      const long long m = (long long)m0 + r;
+      const bool row_ok = m < (long long)p.M;
+      const T* res_row = (p.residual && row_ok) ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
+      const T* b2_row = (p.bias2 && row_ok)
+                            ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2
+                            : nullptr;
+      const T* bias = reinterpret_cast<const T*>(p.bias);
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      const int acc_per_fill = p.glu ? 128 : 64;
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end; c0 += acc_per_fill) {
+        if (lane == 0) tc::tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll 1
+        for (int cc = 0; cc < acc_per_fill; cc += 32) {
+          const int c = c0 + cc;
+          const int col0 = n0 + c;
+          vec8 vb[4], vr[4], vb2[4];
+#pragma unroll
+          for (int gI = 0; gI < 4; ++gI) {
+            const int col = col0 + gI * 8;
+            const bool col_ok = col < p.N;
+            vb[gI] = (bias && col_ok) ? ld_cached16(bias + col) : vec8{0u, 0u, 0u, 0u};
+            vr[gI] = (res_row && col_ok) ? ld_cached16(res_row + col) : vec8{0u, 0u, 0u, 0u};
+            vb2[gI] = (b2_row && col_ok) ? ld_cached16(b2_row + col) : vec8{0u, 0u, 0u, 0u};
+          }
+          uint32_t raw[32];
+          tc::tmem_ld_32x32(taddr + (uint32_t)c, raw);
+          tc::tmem_ld_wait();
+          if (c + 32 >= c_end) {  // accumulator drained: tell the leader's MMA warp (remote arrive on its barrier)
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_remote(&tmem_empty_bar[buf], 0);
+          }
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+#pragma unroll
+          for (int gI = 0; gI < 4; ++gI) {
+            float* vv = v + gI * 8;
+            float bf[8];
+            unpack8<T>(vb[gI], bf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
+            if (p.bias2) {
+              unpack8<T>(vb2[gI], bf);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
+            }
+            if (p.glu == 0) {
+              if (p.act) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(act_apply<T>(vv[i], p.act)));
+              }
+              if (p.residual) {
+                unpack8<T>(vr[gI], bf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] += bf[i];
+              }
+              const int j = (cc >> 3) + gI;
+              *reinterpret_cast<vec8*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8<T>(vv);
+            } else {
+              T o4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float a = vv[2 * i], b = vv[2 * i + 1];
+                float o;
+                if (p.glu == 1)
+                  o = a * ss_num<T>::to_f(ss_num<T>::from_f(gelu_erf(b)));
+                else
+                  o = ss_num<T>::to_f(ss_num<T>::from_f(a / (1.f + __expf(-a)))) * b;
+                o4[i] = ss_num<T>::from_f(o);
+              }
+              const int ocol = (cc + gI * 8) >> 1;
+              const int j = ocol >> 3, within = (ocol & 7) * 2;
+              *reinterpret_cast<uint2*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4) + within) =
+                  *reinterpret_cast<const uint2*>(o4);
+            }
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int out_col = p.glu ? ((n0 + c0) >> 1) : (n0 + c0);
+          const int n_out = p.glu ? (p.N >> 1) : p.N;
+          if (out_col < n_out && (long long)m0 + q * 32 < (long long)p.M)
+            tc::tma_store_2d(&tmC, stg, out_col, m0 + q * 32);
+          tc::tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tc::tma_store_wait_all<0>();
+  }
+
+  tc::fence_before_sync();
+  tc::cluster_sync();  // neither CTA may free TMEM / exit while its peer can still touch the pair's resources
+  if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, 2 * BN);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side: tensor-map construction (driver entry point resolved at run time) + cache
 // ---------------------------------------------------------------------------------------------
@@ -688,6 +951,57 @@ int dispatch_persist(int dtype, int bn, const CUtensorMap& ta, const CUtensorMap
   }
 }
 
+template <typename T, bool CONV>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const GemmParams& p, int n_tiles_n,
+                long long total_pair_tiles, cudaStream_t s) {
+  using L = PairLayout;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<T, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int max_clusters = sm_count() / 2;
+  const int clusters = (int)(total_pair_tiles < max_clusters ? total_pair_tiles : max_clusters);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(GEMM_PERSIST_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  SS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<T, CONV>, ta, tb, tcm, p, n_tiles_n, (int)total_pair_tiles));
+  return 0;
+}
+
+// 0 = never, 1 = when the shape suits (default), 2 = whenever legal
+int pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SS_GEMM_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+// the CTA-pair kernel wants a 256-wide N tile without much padding and enough 256 x 256 tiles to fill the chip
+bool use_pair(long long m_subtiles, int N, int glu, int force_bn) {
+  const int mode = pair_mode();
+  if (mode == 0 || force_bn == 64 || force_bn == 128) return false;
+  if (N < 256) return false;
+  if (mode == 2) return true;
+  const int pad256 = (N + 255) / 256 * 256;
+  if (pad256 * 100 > N * 108) return false;
+  const long long pair_tiles = ((m_subtiles + 1) / 2) * (pad256 / 256);
+  return pair_tiles >= 60;
+}
+
 // N tile for the persistent kernel: 128 unless the problem is narrow; GLU needs >= 128
 int pick_bn_persist(int N, int glu, int force_bn) {
   if (force_bn == 64 || force_bn == 128 || force_bn == 256) return (glu && force_bn == 64) ? 128 : force_bn;
@@ -756,6 +1070,16 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
   if (!legacy) {
     CUtensorMap tcm;
     if (int e = get_out_tmap(&tcm, C, dtype, M, glu ? N / 2 : N, ldc)) return e;
+    if (use_pair(m_tiles, N, glu, force_bn)) {
+      CUtensorMap tb2;
+      uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)ldb * 2};
+      uint32_t box[2] = {BK, 128};
+      if (int e = get_tmap(&tb2, B, dtype, 2, dims, str, box)) return e;
+      const int n_tiles_n = (N + 255) / 256;
+      const long long pair_tiles = ((m_tiles + 1) / 2) * n_tiles_n;
+      if (dtype == SS_F16) return launch_pair<__half, false>(ta, tb2, tcm, p, n_tiles_n, pair_tiles, (cudaStream_t)stream);
+      return launch_pair<__nv_bfloat16, false>(ta, tb2, tcm, p, n_tiles_n, pair_tiles, (cudaStream_t)stream);
+    }
     const int n_tiles_n = (N + bn - 1) / bn;
     return dispatch_persist<false>(dtype, bn, ta, tb, tcm, p, n_tiles_n, m_tiles * n_tiles_n, (cudaStream_t)stream);
   }
@@ -813,6 +1137,16 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
   if (!legacy) {
     CUtensorMap tcm;
     if (int e = get_out_tmap(&tcm, y, dtype, (long long)Nimg * H * W, Cout, Cout)) return e;
+    if (use_pair(m_tiles, Cout, 0, force_bn)) {
+      CUtensorMap tb2;
+      uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout}, str[1] = {(uint64_t)9 * Cin * 2};
+      uint32_t box[2] = {BK, 128};
+      if (int e = get_tmap(&tb2, w, dtype, 2, dims, str, box)) return e;
+      const int n_tiles_n2 = (Cout + 255) / 256;
+      const long long pair_tiles = ((m_tiles + 1) / 2) * n_tiles_n2;
+      if (dtype == SS_F16) return launch_pair<__half, true>(ta, tb2, tcm, p, n_tiles_n2, pair_tiles, (cudaStream_t)stream);
+      return launch_pair<__nv_bfloat16, true>(ta, tb2, tcm, p, n_tiles_n2, pair_tiles, (cudaStream_t)stream);
+    }
     const int n_tiles_n = (Cout + bn - 1) / bn;
     return dispatch_persist<true>(dtype, bn, ta, tb, tcm, p, n_tiles_n, m_tiles * n_tiles_n, (cudaStream_t)stream);
   }
