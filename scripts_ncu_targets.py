@@ -27,6 +27,16 @@ if which in ("all", "gemm"):
         x, w = rnd(Nimg, H, W, Cin), rnd(Cout, 9 * Cin, sc=1 / math.sqrt(9 * Cin))
         for _ in range(3):
             ops.conv3x3(x, w, bias=rnd(Cout))
+if which == "gemm2":
+    for (M, N, K, glu, res) in [(2048, 10240, 1280, 1, 0), (2048, 1280, 1280, 0, 1), (2048, 3840, 1280, 0, 0)]:
+        a, w = rnd(M, K), rnd(N, K, sc=1 / math.sqrt(K))
+        bias = rnd(N)
+        r = rnd(M, N) if res else None
+        for _ in range(2):
+            ops.gemm(a, w, bias=bias, glu=glu, residual=r)
+    q, k, v = rnd(2, 1024, 1280), rnd(2, 1024, 1280), rnd(2, 1024, 1280)
+    for _ in range(2):
+        ops.mha_packed(q, k, v, 20, 0.125)
 if which in ("all", "skinny"):
     for (N, K) in [(12288, 4096), (4096, 4096), (22016, 4096), (4096, 11008), (32066, 4096)]:
         Ws = [rnd(N, K, sc=0.02) for _ in range(3)]
