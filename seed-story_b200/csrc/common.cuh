@@ -119,7 +119,8 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // short FMA chain instead of erff's branchy polynomial — the GELU epilogues are instruction-bound otherwise.
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float t;  // approximate reciprocal (1 MUFU, ~1 ulp): the IEEE-rounded __frcp_rn costs a Newton sequence per element
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
