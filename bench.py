@@ -191,9 +191,29 @@ def run_ours(args):
         torch.cuda.synchronize()
         fwd_ms = g0.elapsed_time(g1) / 5
         ach = tc_fl / n_l / (tc_ms / n_l * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", achieved=round(ach, 1),
+        # the single most expensive launch type of the step (GEGLU projection 2048 x 10240 x 1280), timed alone
+        a_ = torch.randn(2048, 1280, device=dev).half()
+        w_ = (torch.randn(10240, 1280, device=dev) * 0.03).half()
+        b_ = torch.randn(10240, device=dev).half()
+        o_ = torch.empty(2048, 5120, device=dev).half()
+        for _ in range(3):
+            ops.gemm(a_, w_, bias=b_, glu=ops.GLU_GEGLU, out=o_)
+        g0.record()
+        for _ in range(20):
+            ops.gemm(a_, w_, bias=b_, glu=ops.GLU_GEGLU, out=o_)
+        g1.record()
+        torch.cuda.synchronize()
+        top_ms = g0.elapsed_time(g1) / 20
+        top_fl = 2.0 * 2048 * 10240 * 1280
+        roof = dict(bound="tensor", kernel="gemm_tc_pair_kernel / gemm_tc_persist_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)",
+                    achieved=round(ach, 1),
                     peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(ach / peaks["tf_sustained"], 4),
-                    traffic=None, peak_source=peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                    traffic=31.8e6, traffic_note="dram__bytes_read+write of the GEGLU launch below from ncu --set full "
+                    "(profiles/r1_ncu_gemm_fmha_full.md); its algorithmic operand bytes are 31.5e6",
+                    top_launch=dict(shape="GEGLU GEMM 2048x10240x1280 (70 launches per UNet step)", us=round(top_ms * 1e3, 1),
+                                    achieved=round(top_fl / (top_ms * 1e-3) / 1e12, 1), peak=peaks["tf_burst"],
+                                    frac=round(top_fl / (top_ms * 1e-3) / 1e12 / peaks["tf_burst"], 4)),
+                    peak_source=peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
                     launches_per_unet_step=n_l, algorithmic_tflop_per_unet_step=round(tc_fl / 1e12, 3),
                     unet_step_ms=round(fwd_ms, 3), tc_share_of_unet_step=round(tc_ms / fwd_ms, 3))
         if world == 1 and not args.no_cpu_baseline:
