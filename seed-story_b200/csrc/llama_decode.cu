@@ -8,6 +8,8 @@
 //
 // The skinny GEMM streams W once with 16-byte no-allocate loads and uses mma.sync.m16n8k16 purely as
 // a convenient 16x8 dot-product engine (N = 8 batch columns); it is bandwidth-bound by construction.
+#include <cstdlib>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -23,7 +25,7 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-constexpr int SG_WARPS = 8;
+constexpr int SG_WARPS_MAX = 8;
 constexpr int SG_UNROLL = 8;   // k-blocks (32 wide) per register batch; two batches are in flight per warp
 constexpr int SG_ROWS = 8;     // weight rows per CTA
 
@@ -31,12 +33,12 @@ constexpr int SG_ROWS = 8;     // weight rows per CTA
 // (m = batch index, rows 8..15 zero), so a lane streams ONE 16-byte piece of one weight row per 32-wide k-block;
 // the 8 warps interleave over k-blocks, keep two register batches of loads in flight (software pipeline) and
 // reduce their 8x8 partial results through shared memory.
-template <int EPI>
+template <int EPI, int SG_WARPS>
 __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half* __restrict__ x, int ldx,
                                                                     const __half* __restrict__ W,
                                                                     __half* __restrict__ y, int ldy, int B, int N,
                                                                     int K, const __half* __restrict__ res, int ldr) {
-  __shared__ float part[SG_WARPS][8][8];  // [warp][batch][row]
+  __shared__ float part[SG_WARPS_MAX][8][8];  // [warp][batch][row]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * SG_ROWS;
@@ -126,21 +128,32 @@ SS_API int ss_skinny_gemm_f16(const void* x, int ldx, const void* W, void* y, in
   SS_REQUIRE(epilogue != EPI_SWIGLU || N % 8 == 0, "SwiGLU needs N % 8 == 0");
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = ceil_div(N, SG_ROWS);
+  static int warps = 0;
+  if (warps == 0) {
+    const char* e = getenv("SS_SKINNY_WARPS");
+    warps = (e && atoi(e) == 4) ? 4 : 8;
+  }
   const __half *xp = (const __half*)x, *Wp = (const __half*)W, *rp = (const __half*)residual;
   __half* yp = (__half*)y;
   switch (epilogue) {
     case EPI_NONE:
-      SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_NONE>, dim3(grid), dim3(SG_WARPS * 32), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp,
-                             ldr));
+      if (warps == 4)
+        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_NONE, 4>, dim3(grid), dim3(128), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
+      else
+        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_NONE, 8>, dim3(grid), dim3(256), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
       break;
     case EPI_RESIDUAL:
       SS_REQUIRE(residual != nullptr, "residual epilogue needs a residual pointer");
-      SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_RESIDUAL>, dim3(grid), dim3(SG_WARPS * 32), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp,
-                             ldr));
+      if (warps == 4)
+        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_RESIDUAL, 4>, dim3(grid), dim3(128), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
+      else
+        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_RESIDUAL, 8>, dim3(grid), dim3(256), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
       break;
     case EPI_SWIGLU:
-      SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_SWIGLU>, dim3(grid), dim3(SG_WARPS * 32), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp,
-                             ldr));
+      if (warps == 4)
+        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_SWIGLU, 4>, dim3(grid), dim3(128), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
+      else
+        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_SWIGLU, 8>, dim3(grid), dim3(256), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
       break;
     default:
       SS_FAIL("unknown epilogue");
