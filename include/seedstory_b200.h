@@ -100,10 +100,14 @@ SS_EXPORT int ss_kv_gather_tokens_16b(void* kpool, void* vpool, int layers, long
  * epilogue order: +bias[N] -> round -> +bias2[row / rows_per_group, N] -> round -> act (1 gelu-erf,
  * 2 silu) -> round -> +residual -> round.  glu: 1 = first*gelu(second) (diffusers GEGLU), 2 =
  * silu(first)*second (LlamaMLP, :191) over interleaved column pairs, output width N/2.
- * force_bn: 0 = auto, else 64/128/256 (N tile). */
+ * force_bn: 0 = auto, else 64/128/160/256 (N tile).
+ * flags: SS_GEMM_B_CONST = B is a weight matrix that no work queued on `stream` writes (an nn.Linear weight): its
+ * first tiles are then fetched while the preceding kernel is still draining.  Leave it clear when B is an
+ * activation (e.g. the q k^T product of the VAE mid-block attention). */
+#define SS_GEMM_B_CONST 1
 SS_EXPORT int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N,
                          int K, const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr,
-                         int act, int glu, float alpha, int force_bn, void* stream);
+                         int act, int glu, float alpha, int force_bn, int flags, void* stream);
 /* 3x3 / stride 1 / pad 1 convolution on NHWC activations as an implicit GEMM (diffusers ResnetBlock2D
  * conv1/conv2, Up/Downsample convs, VAE decoder convs — SURVEY.md Appendix C).  w is [Cout, 9*Cin] with
  * k = (ky*3+kx)*Cin + c.  bias2 is the per-image time-embedding row [Nimg, Cout]. */

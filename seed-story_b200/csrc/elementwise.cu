@@ -107,6 +107,7 @@ __global__ void groupnorm_partial_kernel(const T* __restrict__ x, float* __restr
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
     const T* base = x + ((size_t)n * HW) * C + v * 8;
+#pragma unroll 4
     for (int p = p0 + lane; p < p1; p += nl) {
       float f[8];
       unpack8<T>(ld_cached16(base + (size_t)p * C), f);
@@ -165,32 +166,46 @@ __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, flo
   }
 }
 
+// apply: same (chunk, image) geometry as the partial kernel, so every thread owns one 8-channel vector — gamma,
+// beta and the (at most eight) group statistics live in registers and the pixel loop has no integer divisions
 template <typename T>
 __global__ void groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
                                        const T* __restrict__ gamma, const T* __restrict__ beta, int HW, int C,
-                                       int groups, int silu, long long total_vecs) {
+                                       int groups, int silu, int pix_per_cta) {
+  const int n = blockIdx.y;
   const int vecs = C >> 3, cg = C / groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vecs;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vecs);
-    const long long pix = i / vecs;
-    const int n = (int)(pix / HW);
-    float f[8], gm[8], bt[8];
-    unpack8<T>(ld_cached16(x + pix * C + v * 8), f);
+  const int nl = blockDim.x / vecs;
+  const int v = threadIdx.x % vecs, lane = threadIdx.x / vecs;
+  if (lane >= nl) return;
+  float sc[8], sh[8];
+  {
+    float gm[8], bt[8];
     unpack8<T>(ld_cached16(gamma + v * 8), gm);
     unpack8<T>(ld_cached16(beta + v * 8), bt);
+    const int c0 = v * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (v * 8 + j) / cg;
-      const float mean = stats[((size_t)n * groups + g) * 2], rstd = stats[((size_t)n * groups + g) * 2 + 1];
-      float o = (f[j] - mean) * rstd * gm[j] + bt[j];
-      if (silu) {
-        o = ss_num<T>::to_f(ss_num<T>::from_f(o));  // GroupNorm output is rounded before the activation module
-        o = o / (1.f + __expf(-o));
-      }
-      f[j] = o;
+      const float* st = stats + ((size_t)n * groups + (c0 + j) / cg) * 2;
+      sc[j] = st[1];  // rstd
+      sh[j] = st[0];  // mean; the pixel loop keeps the order ((x - mean) * rstd) * gamma + beta
     }
-    st16(y + pix * C + v * 8, pack8<T>(f));
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    const size_t base = ((size_t)n * HW) * C + v * 8;
+#pragma unroll 4
+    for (int p = p0 + lane; p < p1; p += nl) {
+      float f[8];
+      unpack8<T>(ld_cached16(x + base + (size_t)p * C), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float o = (f[j] - sh[j]) * sc[j] * gm[j] + bt[j];
+        if (silu) {
+          o = ss_num<T>::to_f(ss_num<T>::from_f(o));  // GroupNorm output is rounded before the activation module
+          o = o / (1.f + __expf(-o));
+        }
+        f[j] = o;
+      }
+      st16(y + base + (size_t)p * C, pack8<T>(f));
+    }
   }
 }
 
@@ -225,7 +240,6 @@ SS_API int ss_groupnorm_nhwc(int dtype, const void* x, void* y, const void* gamm
   SS_REQUIRE(smem <= 48 * 1024, "GroupNorm partial kernel shared memory");
   float* stats = stats_ws;
   float* partial = stats_ws + 2 * N * groups;
-  const long long total_vecs = (long long)N * HW * vecs;
   const float inv_cnt = 1.f / ((float)HW * (float)(C / groups));
   if (dtype == SS_F16)
     groupnorm_partial_kernel<__half><<<dim3(chunks, N), block, smem, s>>>((const __half*)x, partial, HW, C, groups,
@@ -238,12 +252,12 @@ SS_API int ss_groupnorm_nhwc(int dtype, const void* x, void* y, const void* gamm
                                                                    N * groups);
   SS_LAUNCH_CHECK();
   if (dtype == SS_F16)
-    groupnorm_apply_kernel<__half><<<ew_grid(total_vecs), EW_THREADS, 0, s>>>(
-        (const __half*)x, (__half*)y, stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, silu, total_vecs);
+    groupnorm_apply_kernel<__half><<<dim3(chunks, N), block, 0, s>>>(
+        (const __half*)x, (__half*)y, stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, silu, pix_per_cta);
   else
-    groupnorm_apply_kernel<__nv_bfloat16><<<ew_grid(total_vecs), EW_THREADS, 0, s>>>(
+    groupnorm_apply_kernel<__nv_bfloat16><<<dim3(chunks, N), block, 0, s>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, stats, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, HW,
-        C, groups, silu, total_vecs);
+        C, groups, silu, pix_per_cta);
   SS_LAUNCH_CHECK();
   return 0;
 }

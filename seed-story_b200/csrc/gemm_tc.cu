@@ -36,6 +36,7 @@ struct GemmParams {
   int glu;  // 0 none, 1 first*gelu(second), 2 silu(first)*second   (column pairs interleaved)
   float alpha;
   int M, N, K;
+  int b_const;  // B is a weight matrix nothing on the stream writes: its first tiles may be fetched before the PDL wait
   // conv mode
   int H, W, Cin, bw, bh, tiles_x, tiles_y;
 };
@@ -252,11 +253,15 @@ template <int BN>
 struct PersistLayout {
   // a stage holds KATOMS k-atoms of 64 elements: wide stages amortise the per-stage barrier round trip of the
   // single MMA-issuing thread when the N tile (and with it the tensor-core time per atom) is small
-  static constexpr int KATOMS = (BN == 256) ? 1 : 2;
+  static constexpr int KATOMS = (BN >= 160) ? 1 : 2;
   static constexpr int A_BYTES = BM * BK * 2;   // per atom
   static constexpr int B_BYTES = BN * BK * 2;   // per atom
   static constexpr int STAGE_BYTES = KATOMS * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 160 ? 5 : (BN == 128 ? 3 : 4));
+  // TMEM: two accumulators; the 160-wide tile (every SDXL channel count is a multiple of 160) keeps them on
+  // 256-column boundaries, and allocations must be powers of two
+  static constexpr int TMEM_STRIDE = (BN == 160) ? 256 : BN;
+  static constexpr int TMEM_COLS = 2 * TMEM_STRIDE;
   static constexpr int STAGING_BYTES = 8 /*epilogue warps*/ * 32 * 128;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
       tc::fence_barrier_init();
     }
     __syncwarp();
-    tc::tmem_alloc(tmem_ptr_smem, 2 * BN);
+    tc::tmem_alloc(tmem_ptr_smem, L::TMEM_COLS);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -331,7 +336,31 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      pdl_wait();  // A (and everything the epilogue reads) is produced by earlier kernels in the stream
+      // The B operand of a linear layer / convolution is a weight matrix no kernel writes, so the first pipeline
+      // fill of B is requested BEFORE waiting on the preceding kernel: the HBM latency of the weights then overlaps
+      // that kernel's tail.  A (and everything the epilogue reads) is produced by earlier kernels in the stream.
+      int pre = 0;
+      if (p.b_const && (int)blockIdx.x < total_tiles) {
+        int n0, m0, img, y0, x0;
+        tile_coords(blockIdx.x, n0, m0, img, y0, x0);
+        pre = min(L::STAGES, num_kb);
+        for (int kb = 0; kb < pre; ++kb) {
+          uint8_t* stage = smem + kb * L::STAGE_BYTES;
+          const int na = min(L::KATOMS, num_atoms - kb * L::KATOMS);
+          tc::mbar_expect_tx(&full_bar[kb], na * (L::A_BYTES + L::B_BYTES));
+          for (int a = 0; a < na; ++a) {
+            const int atom = kb * L::KATOMS + a;
+            uint8_t* sb = stage + a * (L::A_BYTES + L::B_BYTES) + L::A_BYTES;
+            if (CONV) {
+              const int tap = atom / kchunks, c0 = (atom % kchunks) * BK;
+              tc::tma_load_2d(sb, &tmB, &full_bar[kb], tap * p.Cin + c0, n0);
+            } else {
+              tc::tma_load_2d(sb, &tmB, &full_bar[kb], atom * BK, n0);
+            }
+          }
+        }
+      }
+      pdl_wait();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n0, m0, img, y0, x0;
@@ -339,10 +368,13 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % L::STAGES;
           const uint32_t ph = (it / L::STAGES) & 1;
-          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          const bool b_done = (int)it < pre;  // this stage's barrier is armed and its B tile already in flight
           uint8_t* stage = smem + s * L::STAGE_BYTES;
           const int na = min(L::KATOMS, num_atoms - kb * L::KATOMS);
-          tc::mbar_expect_tx(&full_bar[s], na * (L::A_BYTES + L::B_BYTES));
+          if (!b_done) {
+            tc::mbar_wait(&empty_bar[s], ph ^ 1);
+            tc::mbar_expect_tx(&full_bar[s], na * (L::A_BYTES + L::B_BYTES));
+          }
           for (int a = 0; a < na; ++a) {
             const int atom = kb * L::KATOMS + a;
             uint8_t* sa = stage + a * (L::A_BYTES + L::B_BYTES);
@@ -351,10 +383,10 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
               const int tap = atom / kchunks, c0 = (atom % kchunks) * BK;
               const int ky = tap / 3, kx = tap % 3;
               tc::tma_load_4d(sa, &tmA, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, img);
-              tc::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.Cin + c0, n0);
+              if (!b_done) tc::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.Cin + c0, n0);
             } else {
               tc::tma_load_2d(sa, &tmA, &full_bar[s], atom * BK, m0);
-              tc::tma_load_2d(sb, &tmB, &full_bar[s], atom * BK, n0);
+              if (!b_done) tc::tma_load_2d(sb, &tmB, &full_bar[s], atom * BK, n0);
             }
           }
         }
@@ -369,7 +401,7 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
         const uint32_t buf = lt & 1, use = lt >> 1;
         tc::mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
         tc::fence_after_sync();
-        const uint32_t tmem_d = tmem_base + buf * BN;
+        const uint32_t tmem_d = tmem_base + buf * L::TMEM_STRIDE;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % L::STAGES;
           const uint32_t ph = (it / L::STAGES) & 1;
@@ -398,19 +430,20 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
     const int r = q * 32 + lane;
     uint8_t* stg = staging + ((grp * 4 + q) * (32 * 128));
     pdl_wait();  // residual / bias2 come from earlier kernels; our stores must not overtake their readers
-    // one-tile CTAs (small problems): nothing to overlap with, so both groups split that tile's columns instead
-    const int acc_per_fill_k = p.glu ? 128 : 64;
-    const bool split_cols = (total_tiles <= (int)gridDim.x) && (BN / 2 >= acc_per_fill_k);
+    // one staging fill = 64 output columns (128 bytes per row): 64 accumulator columns, or 128 with a GLU.  A
+    // 160-wide tile ends in a 32-column tail fill that is written straight from registers.
+    const int acc_per_fill = p.glu ? 128 : 64;
+    constexpr int kTail = BN % 64;  // 32 for BN = 160, else 0 (a GLU tail is BN % 128 = 32 as well)
+    const int nfills = (BN + acc_per_fill - 1) / acc_per_fill;
+    // one-tile CTAs (small problems): nothing to overlap with, so the two groups take alternate fills of that tile
+    const bool split_cols = (total_tiles <= (int)gridDim.x) && nfills >= 2;
+    const int f_begin = split_cols ? grp : 0, f_step = split_cols ? 2 : 1;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       if (!split_cols && (int)(lt & 1) != grp) continue;
-      const int c_begin = split_cols ? grp * (BN / 2) : 0;
-      const int c_end = split_cols ? (grp + 1) * (BN / 2) : BN;
       int n0, m0, img, y0, x0;
       tile_coords(tile, n0, m0, img, y0, x0);
       const uint32_t buf = lt & 1, use = lt >> 1;
-      tc::mbar_wait(&tmem_full_bar[buf], use & 1);
-      tc::fence_after_sync();
       const long long m = (long long)m0 + r;
       const bool row_ok = m < (long long)p.M;
       const T* res_row = (p.residual && row_ok) ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
@@ -418,32 +451,56 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
                             ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2
                             : nullptr;
       const T* bias = reinterpret_cast<const T*>(p.bias);
-      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + buf * L::TMEM_STRIDE + ((uint32_t)(q * 32) << 16);
+      T* out_row = reinterpret_cast<T*>(p.out) + m * p.ldo;
+      const int n_out_cols = p.glu ? (p.N >> 1) : p.N;
 
-      // one staging fill = 64 output columns (128 bytes per row): 64 accumulator columns, or 128 with a GLU
-      const int acc_per_fill = p.glu ? 128 : 64;
+      // the residual of a 32-column chunk is requested one chunk ahead (the first one before the accumulator is
+      // even complete), so its global-memory latency hides behind the main loop and the previous chunk
+      vec8 nr[4];
+      auto request = [&](int col0) {
+#pragma unroll
+        for (int gI = 0; gI < 4; ++gI) {
+          const int col = col0 + gI * 8;
+          nr[gI] = (res_row && col < p.N) ? ld_cached16(res_row + col) : vec8{0u, 0u, 0u, 0u};
+        }
+      };
+      if (f_begin < nfills) request(n0 + f_begin * acc_per_fill);
+      tc::mbar_wait(&tmem_full_bar[buf], use & 1);
+      tc::fence_after_sync();
+
 #pragma unroll 1
-      for (int c0 = c_begin; c0 < c_end; c0 += acc_per_fill) {
-        if (lane == 0) tc::tma_store_wait_read<0>();  // the previous store from this buffer has been read out
-        __syncwarp();
+      for (int f = f_begin; f < nfills; f += f_step) {
+        const int c0 = f * acc_per_fill;
+        const int fill_cols = min(acc_per_fill, BN - c0);
+        const bool direct = kTail != 0 && fill_cols < acc_per_fill;  // tail: registers -> global, no staging
+        const bool last_fill = f + f_step >= nfills;
+        if (!direct) {
+          if (lane == 0) tc::tma_store_wait_read<0>();  // the previous store from this buffer has been read out
+          __syncwarp();
+        }
 #pragma unroll 1
-        for (int cc = 0; cc < acc_per_fill; cc += 32) {
+        for (int cc = 0; cc < fill_cols; cc += 32) {
           const int c = c0 + cc;
           const int col0 = n0 + c;
-          // issue every global load of this chunk up front (independent requests, one exposed latency)
           vec8 vb[4], vr[4], vb2[4];
 #pragma unroll
           for (int gI = 0; gI < 4; ++gI) {
+            vr[gI] = nr[gI];
             const int col = col0 + gI * 8;
             const bool col_ok = col < p.N;
             vb[gI] = (bias && col_ok) ? ld_cached16(bias + col) : vec8{0u, 0u, 0u, 0u};
-            vr[gI] = (res_row && col_ok) ? ld_cached16(res_row + col) : vec8{0u, 0u, 0u, 0u};
             vb2[gI] = (b2_row && col_ok) ? ld_cached16(b2_row + col) : vec8{0u, 0u, 0u, 0u};
+          }
+          {  // next chunk of this warp: same fill, or the first chunk of its next fill
+            int nf = f, ncc = cc + 32;
+            if (ncc >= fill_cols) nf = f + f_step, ncc = 0;
+            if (nf < nfills) request(n0 + nf * acc_per_fill + ncc);
           }
           uint32_t raw[32];
           tc::tmem_ld_32x32(taddr + (uint32_t)c, raw);
           tc::tmem_ld_wait();
-          if (c + 32 >= c_end) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
+          if (last_fill && cc + 32 >= fill_cols) {  // last TMEM read of this tile: hand the accumulator back
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[buf]);
@@ -473,9 +530,13 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vv[i] += bf[i];
               }
-              // 16-byte piece j of this row inside the 128-byte staging row, 128B-swizzled like the TMA expects
-              const int j = (cc >> 3) + gI;
-              *reinterpret_cast<vec8*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8<T>(vv);
+              if (direct) {
+                if (row_ok && col0 + gI * 8 < p.N) st16(out_row + col0 + gI * 8, pack8<T>(vv));
+              } else {
+                // 16-byte piece j of this row inside the 128-byte staging row, 128B-swizzled like the TMA expects
+                const int j = (cc >> 3) + gI;
+                *reinterpret_cast<vec8*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8<T>(vv);
+              }
             } else {
               T o4[4];
 #pragma unroll
@@ -490,18 +551,24 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
               }
               // 8 accumulator columns -> 4 outputs = 8 bytes; output column within the fill = (cc + gI*8) / 2
               const int ocol = (cc + gI * 8) >> 1;               // 0..63
-              const int j = ocol >> 3, within = (ocol & 7) * 2;  // 16-byte piece, byte offset inside it
-              *reinterpret_cast<uint2*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4) + within) =
-                  *reinterpret_cast<const uint2*>(o4);
+              if (direct) {
+                const int gcol = ((n0 + c0) >> 1) + ocol;
+                if (row_ok && gcol < n_out_cols)
+                  *reinterpret_cast<uint2*>(out_row + gcol) = *reinterpret_cast<const uint2*>(o4);
+              } else {
+                const int j = ocol >> 3, within = (ocol & 7) * 2;  // 16-byte piece, byte offset inside it
+                *reinterpret_cast<uint2*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4) + within) =
+                    *reinterpret_cast<const uint2*>(o4);
+              }
             }
           }
         }
+        if (direct) continue;
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           const int out_col = p.glu ? ((n0 + c0) >> 1) : (n0 + c0);
-          const int n_out = p.glu ? (p.N >> 1) : p.N;
-          if (out_col < n_out && (long long)m0 + q * 32 < (long long)p.M)
+          if (out_col < n_out_cols && (long long)m0 + q * 32 < (long long)p.M)
             tc::tma_store_2d(&tmC, stg, out_col, m0 + q * 32);
           tc::tma_store_commit();
         }
@@ -512,7 +579,7 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
 
@@ -943,10 +1010,12 @@ int dispatch_persist(int dtype, int bn, const CUtensorMap& ta, const CUtensorMap
   if (dtype == SS_F16) {
     if (bn == 64) return launch_persist<__half, 64, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
     if (bn == 128) return launch_persist<__half, 128, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
+    if (bn == 160) return launch_persist<__half, 160, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
     return launch_persist<__half, 256, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
   } else {
     if (bn == 64) return launch_persist<__nv_bfloat16, 64, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
     if (bn == 128) return launch_persist<__nv_bfloat16, 128, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
+    if (bn == 160) return launch_persist<__nv_bfloat16, 160, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
     return launch_persist<__nv_bfloat16, 256, CONV>(ta, tb, tcm, p, n_tiles_n, total_tiles, s);
   }
 }
@@ -990,25 +1059,58 @@ int pair_mode() {
   return v;
 }
 
+// Tile selection by a wave-quantisation cost model, in units of "accumulator columns of tensor-core time":
+// a launch costs waves x (BN x smem-boundness + a fixed per-tile term).  The 160-wide tile exists because every
+// SDXL channel count (320, 640, 1280, 2560, 5120, 10240) is a multiple of 160 but not always of 256, and
+// M = 2048 rows x N = 1280 is 80 tiles of 256 (half the SMs idle) but 128 tiles of 160.
+long long tile_cost(long long m_tiles, int N, int bn) {
+  const long long tiles = m_tiles * ((N + bn - 1) / bn);
+  const long long waves = (tiles + sm_count() - 1) / sm_count();
+  const int eff = bn == 64 ? 150 : (bn == 128 ? 108 : 100);  // narrow tiles are shared-memory-bandwidth bound
+  return waves * (bn * eff + 24 * 100);
+}
+
+long long pair_cost(long long m_tiles, int N) {
+  const long long tiles = ((m_tiles + 1) / 2) * ((N + 255) / 256);
+  const long long clusters = sm_count() / 2;
+  const long long waves = (tiles + clusters - 1) / clusters;
+  return waves * (256 * 95 + 24 * 100);
+}
+
+// N tile for the persistent kernel; a GLU epilogue pairs columns inside a 128-column fill, so it needs >= 128
+int pick_bn_persist(long long m_tiles, int N, int glu, int force_bn) {
+  if (force_bn == 64 || force_bn == 128 || force_bn == 160 || force_bn == 256)
+    return (glu && force_bn == 64) ? 128 : force_bn;
+  if (N <= 64 && !glu) return 64;
+  int best = 256;
+  long long best_cost = tile_cost(m_tiles, N, 256);
+  static int mode160 = -1;  // SS_GEMM_TILE160: 0 never, 1 cost model, 2 (default) cost model but not under a GLU, whose
+                            // register-stored tail measured slower than the 256-wide / CTA-pair kernels
+  if (mode160 < 0) {
+    const char* e = getenv("SS_GEMM_TILE160");
+    mode160 = e ? atoi(e) : 2;
+  }
+  const int cands[2] = {160, 128};
+  for (int c : cands) {
+    if (c == 160 && (mode160 == 0 || (mode160 == 2 && glu))) continue;
+    const long long k = tile_cost(m_tiles, N, c);
+    if (k < best_cost) best = c, best_cost = k;
+  }
+  return best;
+}
+
 // the CTA-pair kernel wants a 256-wide N tile without much padding and enough 256 x 256 tiles to fill the chip
-bool use_pair(long long m_subtiles, int N, int glu, int force_bn) {
+bool use_pair(long long m_tiles, int N, int glu, int force_bn) {
   const int mode = pair_mode();
-  if (mode == 0 || force_bn == 64 || force_bn == 128) return false;
+  if (mode == 0 || force_bn == 64 || force_bn == 128 || force_bn == 160) return false;
   if (N < 256) return false;
   if (mode == 2) return true;
   const int pad256 = (N + 255) / 256 * 256;
   if (pad256 * 100 > N * 108) return false;
-  const long long pair_tiles = ((m_subtiles + 1) / 2) * (pad256 / 256);
-  return pair_tiles >= 60;
-}
-
-// N tile for the persistent kernel: 128 unless the problem is narrow; GLU needs >= 128
-int pick_bn_persist(int N, int glu, int force_bn) {
-  if (force_bn == 64 || force_bn == 128 || force_bn == 256) return (glu && force_bn == 64) ? 128 : force_bn;
-  if (N <= 64 && !glu) return 64;
-  // wider N tiles halve the B-operand traffic and the MMA issue overhead; take 256 unless it pads N much more
-  const int pad256 = (N + 255) / 256 * 256, pad128 = (N + 127) / 128 * 128;
-  return (pad256 * 100 <= pad128 * 108) ? 256 : 128;
+  const long long pair_tiles = ((m_tiles + 1) / 2) * (pad256 / 256);
+  if (pair_tiles < 60) return false;
+  if (force_bn == 256) return true;
+  return pair_cost(m_tiles, N) <= tile_cost(m_tiles, N, pick_bn_persist(m_tiles, N, glu, 0));
 }
 
 int get_out_tmap(CUtensorMap* out, const void* C, int dtype, long long M, int n_out, int ldc) {
@@ -1031,7 +1133,7 @@ int pick_bn(long long m_tiles, int N, int force_bn) {
 // C[M,N] = epi(alpha * A[M,K] B[N,K]^T); see include/seedstory_b200.h for the argument contract.
 SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                       const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr, int act,
-                      int glu, float alpha, int force_bn, void* stream) {
+                      int glu, float alpha, int force_bn, int flags, void* stream) {
   SS_REQUIRE(dtype == SS_F16 || dtype == SS_BF16, "dtype must be f16 or bf16");
   SS_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
   SS_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "N, K, lda, ldb, ldc % 8");
@@ -1039,7 +1141,7 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
   SS_REQUIRE(bias2 == nullptr || rows_per_group > 0, "bias2 needs rows_per_group");
   const long long m_tiles = (M + BM - 1) / BM;
   const bool legacy = use_legacy();
-  const int bn = legacy ? pick_bn(m_tiles, N, force_bn) : pick_bn_persist(N, glu, force_bn);
+  const int bn = legacy ? pick_bn(m_tiles, N, force_bn) : pick_bn_persist(m_tiles, N, glu, force_bn);
   CUtensorMap ta, tb;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)lda * 2};
@@ -1067,6 +1169,7 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
   p.M = M;
   p.N = N;
   p.K = K;
+  p.b_const = (flags & 1 /* SS_GEMM_B_CONST */) ? 1 : 0;
   if (!legacy) {
     CUtensorMap tcm;
     if (int e = get_out_tmap(&tcm, C, dtype, M, glu ? N / 2 : N, ldc)) return e;
@@ -1099,7 +1202,7 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
   SS_REQUIRE(bw * bh == BM && W % bw == 0 && H % bh == 0, "image must tile into 128-pixel boxes");
   const long long m_tiles = (long long)Nimg * (H / bh) * (W / bw);
   const bool legacy = use_legacy();
-  const int bn = legacy ? pick_bn(m_tiles, Cout, force_bn) : pick_bn_persist(Cout, 0, force_bn);
+  const int bn = legacy ? pick_bn(m_tiles, Cout, force_bn) : pick_bn_persist(m_tiles, Cout, 0, force_bn);
   CUtensorMap ta, tb;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
@@ -1127,6 +1230,7 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
   p.M = Nimg * H * W;
   p.N = Cout;
   p.K = 9 * Cin;
+  p.b_const = 1;  // convolution weights
   p.H = H;
   p.W = W;
   p.Cin = Cin;

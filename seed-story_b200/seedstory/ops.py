@@ -169,8 +169,9 @@ GLU_NONE, GLU_GEGLU, GLU_SWIGLU = 0, 1, 2
 
 
 def gemm(a, w, bias=None, bias2=None, rows_per_group=0, residual=None, act=ACT_NONE, glu=GLU_NONE, alpha=1.0,
-         out=None, force_bn=0):
-    """out[M, N or N/2] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores."""
+         out=None, force_bn=0, w_const=True):
+    """out[M, N or N/2] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores.  w_const: `w` is a weight matrix that
+    nothing queued on the stream writes (SS_GEMM_B_CONST); pass False when `w` is an activation."""
     _req_cuda(a, w)
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
     assert a.stride(1) == 1 and w.stride(1) == 1
@@ -183,8 +184,8 @@ def gemm(a, w, bias=None, bias2=None, rows_per_group=0, residual=None, act=ACT_N
     _e = _prof_begin()
     _capi.call("ss_gemm_tn", _dt(a), _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
                _p(bias), _p(bias2), rows_per_group, _p(residual), residual.stride(0) if residual is not None else 0,
-               act, glu, ctypes.c_float(alpha), force_bn, _stream())
-    _prof_end(_e, "gemm", 2.0 * M * N * K)
+               act, glu, ctypes.c_float(alpha), force_bn, 1 if w_const else 0, _stream())
+    _prof_end(_e, f"gemm {M}x{N}x{K}" + (" glu" if glu else ""), 2.0 * M * N * K)
     return out
 
 
@@ -205,7 +206,7 @@ def conv3x3(x, w, bias=None, bias2=None, residual=None, act=ACT_NONE, out=None, 
     _e = _prof_begin()
     _capi.call("ss_conv3x3_nhwc", _dt(x), _p(x), _p(w), _p(out), Nimg, H, W_, Cin, Cout, _p(bias), _p(bias2),
                bias2.stride(0) if bias2 is not None else 0, _p(residual), act, force_bn, _stream())
-    _prof_end(_e, "conv3x3", 2.0 * Nimg * H * W_ * Cout * 9 * Cin)
+    _prof_end(_e, f"conv3x3 {Nimg}x{H}x{W_} {Cin}->{Cout}", 2.0 * Nimg * H * W_ * Cout * 9 * Cin)
     return out
 
 

@@ -392,10 +392,10 @@ class VAEDecoderEngine:
         M = H * W
         n = self._gn(h, self.attn["norm"], False).view(M, C)
         qkv = ops.gemm(n, self.attn["qkv"][0], bias=self.attn["qkv"][1])  # [M, 3C]
-        scores = ops.gemm(qkv[:, :C], qkv[:, C:2 * C], alpha=1.0)           # [M, M] = q k^T
+        scores = ops.gemm(qkv[:, :C], qkv[:, C:2 * C], alpha=1.0, w_const=False)           # [M, M] = q k^T
         ops.softmax_rows_(scores, 1.0 / math.sqrt(C))
         vt = ops.transpose2d(qkv[:, 2 * C:].contiguous())                    # [C, M]
-        o = ops.gemm(scores, vt)                                             # [M, C]
+        o = ops.gemm(scores, vt, w_const=False)                                           # [M, C]
         h = ops.gemm(o, self.attn["out"][0], bias=self.attn["out"][1], residual=h.view(M, C)).view(N, H, W, C)
         self.launches += 6
         h = self._res(self.mid1, h)

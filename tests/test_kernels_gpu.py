@@ -168,41 +168,47 @@ def test_gemm_tn_shapes(cuda_dev, dt):
     torch.manual_seed(3)
     tol = 2e-3 if dt == torch.float16 else 1.6e-2
     shapes = [(128, 128, 64), (128, 256, 512), (200, 320, 328), (1041, 4096, 4096), (1024, 4992, 1664),
-              (64, 4096, 4096), (4096, 640, 640), (333, 72, 200)]
+              (64, 4096, 4096), (4096, 640, 640), (333, 72, 200), (2048, 1280, 1280), (300, 168, 136)]
     for (M, N, K) in shapes:
         a = torch.randn(M, K, device=cuda_dev).to(dt)
         w = (torch.randn(N, K, device=cuda_dev) / math.sqrt(K)).to(dt)
         ref = a.float() @ w.float().t()
-        for bn in (0, 64, 128, 256):
+        for bn in (0, 64, 128, 160, 256):
             c = ops.gemm(a, w, force_bn=bn)
             _close(c, ref, rtol=tol, atol=tol * ref.abs().max().item(), what=f"gemm {M}x{N}x{K} bn={bn} {dt}")
 
 
-def test_gemm_tn_epilogues(cuda_dev):
+@pytest.mark.parametrize("bn,M", [(0, 300), (160, 300), (160, 128 * 150 + 17), (256, 300)])
+def test_gemm_tn_epilogues(cuda_dev, bn, M):
+    """Every epilogue, on the auto tile, the 160-wide tile with one tile per CTA (the two epilogue groups take
+    alternate fills + the register-stored tail) and with several tiles per CTA (groups alternate tiles)."""
     from seedstory import ops
+    import functools
     torch.manual_seed(4)
-    M, N, K = 300, 640, 320
+    N, K = 640, 320
+    ops_gemm = functools.partial(ops.gemm, force_bn=bn)
     a = torch.randn(M, K, device=cuda_dev).half()
     w = (torch.randn(N, K, device=cuda_dev) / math.sqrt(K)).half()
     bias = torch.randn(N, device=cuda_dev).half()
     res = torch.randn(M, N, device=cuda_dev).half()
+    rpg = (M + 2) // 3
     b2 = torch.randn(3, N, device=cuda_dev).half()
     lin = (a.float() @ w.float().t() + bias.float()).half()
-    c = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, residual=res)
+    c = ops_gemm(a, w, bias=bias, act=ops.ACT_GELU, residual=res)
     ref = torch.nn.functional.gelu(lin.float()).half().float() + res.float()
     _close(c, ref, what="bias+gelu+res")
-    c = ops.gemm(a, w, bias=bias, bias2=b2, rows_per_group=100, act=ops.ACT_SILU)
-    ref = torch.nn.functional.silu((lin.float() + b2.float().repeat_interleave(100, 0)).half().float())
+    c = ops_gemm(a, w, bias=bias, bias2=b2, rows_per_group=rpg, act=ops.ACT_SILU)
+    ref = torch.nn.functional.silu((lin.float() + b2.float().repeat_interleave(rpg, 0)[:M]).half().float())
     _close(c, ref, what="bias+bias2+silu")
-    c = ops.gemm(a, w, alpha=0.125)
+    c = ops_gemm(a, w, alpha=0.125)
     _close(c, 0.125 * (a.float() @ w.float().t()), what="alpha")
     # GLU epilogues over interleaved column pairs
     wp = w.view(2, N // 2, K).permute(1, 0, 2).reshape(N, K).contiguous()          # rows (first_j, second_j)
     bp = bias.view(2, N // 2).t().reshape(N).contiguous()
     first, second = lin[:, : N // 2], lin[:, N // 2:]
-    c = ops.gemm(a, wp, bias=bp, glu=ops.GLU_GEGLU)
+    c = ops_gemm(a, wp, bias=bp, glu=ops.GLU_GEGLU)
     _close(c, first.float() * torch.nn.functional.gelu(second.float()).half().float(), what="geglu")
-    c = ops.gemm(a, wp, bias=bp, glu=ops.GLU_SWIGLU)
+    c = ops_gemm(a, wp, bias=bp, glu=ops.GLU_SWIGLU)
     _close(c, torch.nn.functional.silu(first.float()).half().float() * second.float(), what="swiglu")
 
 
@@ -223,6 +229,11 @@ def test_conv3x3(cuda_dev, dt):
         w_p = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
         y = ops.conv3x3(x_nhwc, w_p, bias=bias)
         _close(y.permute(0, 3, 1, 2), ref, rtol=tol, atol=tol * ref.abs().max().item(), what=f"conv {H}x{W} {Cin}->{Cout}")
+        if Cout % 160 == 0:
+            y = ops.conv3x3(x_nhwc, w_p, bias=bias, force_bn=256)
+            _close(y.permute(0, 3, 1, 2), ref, rtol=tol, atol=tol * ref.abs().max().item(), what="conv bn=256")
+            y = ops.conv3x3(x_nhwc, w_p, bias=bias, force_bn=160)
+            _close(y.permute(0, 3, 1, 2), ref, rtol=tol, atol=tol * ref.abs().max().item(), what="conv bn=160")
         y = ops.conv3x3(x_nhwc, w_p, bias=bias, bias2=temb, residual=res)
         ref2 = (ref.to(dt).float() + temb.float()[:, :, None, None]).to(dt).float() + res.permute(0, 3, 1, 2).float()
         _close(y.permute(0, 3, 1, 2), ref2, rtol=tol, atol=tol * ref2.abs().max().item(), what="conv+temb+res")
