@@ -43,6 +43,10 @@ if which in ("all", "skinny"):
         x = rnd(1, K)
         for W_ in Ws:
             ops.skinny_gemm(x, W_)
+if which == "fmha1":
+    q, k, v = rnd(2, 4096, 640), rnd(2, 4096, 640), rnd(2, 4096, 640)
+    for _ in range(2):
+        ops.mha_packed(q, k, v, 10, 0.125)
 if which in ("all", "attn"):
     for (B, H, L, D) in [(2, 10, 4096, 64), (2, 20, 1024, 64), (1, 16, 1024, 128)]:
         q, k, v = rnd(B, L, H * D), rnd(B, L, H * D), rnd(B, L, H * D)

@@ -7,18 +7,21 @@
 //                 writes its fp16 P slice (= one 128B-swizzled 64-key atom) for the next MMA
 //   PV = P V      tcgen05.mma  M=128 x N=D x K=128 with V as an MN-major B operand straight from the [key][d]
 //                 layout TMA delivers; the per-tile product is read back and folded into the fp32 running output
-//                 held in registers (O = O * corr + PV), so no TMEM rescale pass is needed
+//                 held in registers (O = (O + PV_{j-1}) * corr_j), so no TMEM rescale pass is needed.  With
+//                 head_dim 64 the P V / row-sum accumulators are double-buffered in TMEM, so tile j-1's product is
+//                 folded in AFTER tile j's probabilities have been handed to the tensor core (off the critical path)
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = softmax + output.
 // Same mask semantics as fmha.cu: causal diagonal anchored bottom-right (xformers LowerTriangularFromBottomRightMask,
 // modeling_llama_xformer.py:289-295), keys >= Lk masked.  Operands are row-matrix views (token rows, heads side by
 // side in a row) so fused QKV buffers are consumed in place.
+#include <cstdlib>
 #include <cstring>
 
 #include "tc.cuh"
 
 namespace {
 
-constexpr int FT_BM = 128, FT_BN = 128, FT_THREADS = 320;  // TMA + MMA warps, 8 softmax warps
+constexpr int FT_BM = 128, FT_BN = 128, FT_THREADS = 576;  // TMA + MMA warps, 16 softmax warps
 
 struct FtParams {
   __half* o;
@@ -29,17 +32,35 @@ struct FtParams {
   int q_col0, k_col0, v_col0;
   float scale_log2;
   int causal;
+  int defer, stages, poly;
 };
+
+// 2^x for x <= 0 on the FMA / integer pipes: round-to-nearest split x = xi + xf (magic-number add), a degree-3
+// minimax polynomial for 2^xf on [-0.5, 0.5] (max relative error 7.5e-5, below half an fp16 ulp — the result is
+// rounded to fp16 right away), and xi added straight into the exponent field.  Inputs below -126 (masked keys are
+// -inf) clamp to 2^-126, which rounds to 0 in fp16.
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;  // 1.5 * 2^23: the low mantissa bits of t now hold round(x)
+  const float xf = x - (t - 12582912.f);
+  float pl = fmaf(xf, 0.0551716685f, 0.2426111251f);
+  pl = fmaf(pl, xf, 0.6932609677f);
+  pl = fmaf(pl, xf, 0.9999280572f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
 
 template <int D>
 struct FtSmem {
   static constexpr int ATOM = 128 * 128;            // [128 rows][64 x 16-bit] = 16 KB
   static constexpr int Q_BYTES = (D / 64) * ATOM;
   static constexpr int KV_BYTES = (D / 64) * ATOM;  // K tile or V tile
-  static constexpr int P_BYTES = 2 * ATOM;
-  static constexpr int STAGES = 2;
+  static constexpr int P_BYTES = 2 * ATOM;          // one P tile; D = 64 keeps two (see kDefer)
+  static constexpr int P_BUFS = (D == 64) ? 2 : 1;
+  // K/V stages: a tile's K/V can only be requested once the P V product two (STAGES) tiles back has retired, so two
+  // stages leave the TMA latency exposed on every tile; head_dim 64 has the shared memory for four
+  static constexpr int STAGES = (D == 64) ? 4 : 2;
   static constexpr int ONES_BYTES = 4096;           // [16][128] fp16 ones: B operand of the row-sum MMA
-  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + ONES_BYTES + 1024 + 256 + 2048 /*row-max exchange*/;
+  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BUFS * P_BYTES + ONES_BYTES + 1024 + 256 + 2048 /*row-max exchange*/;
 };
 
 // MN-major B operand (V as [key][d] rows of 128 bytes, 128B swizzle): SBO = 8 key rows * 128 B, LBO = distance between
@@ -65,17 +86,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + S::Q_BYTES;                       // stage s: K at s*2*KV, V right after
   uint8_t* sP = sKV + S::STAGES * 2 * S::KV_BYTES;
-  uint8_t* sOnes = sP + S::P_BYTES;
+  uint8_t* sOnes = sP + S::P_BUFS * S::P_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + S::ONES_BYTES);
   uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;      // [2]
-  uint64_t* s_empty = bars + 7;     // [2]
-  uint64_t* p_full = bars + 9;      // 1
-  uint64_t* pv_full = bars + 10;    // 1
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
-  float* xchg = reinterpret_cast<float*>(bars + 16);  // [2 halves][128 rows] row-max exchange
+  uint64_t* kv_full = bars + 1;     // [4]
+  uint64_t* kv_empty = bars + 5;    // [4]
+  uint64_t* s_full = bars + 9;      // [2]
+  uint64_t* s_empty = bars + 11;    // [2]
+  uint64_t* p_full = bars + 13;     // 1
+  uint64_t* pv_full = bars + 14;    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  float* xchg = reinterpret_cast<float*>(bars + 20);  // [4 parts][128 rows] row-max exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * FT_BM;
@@ -96,14 +117,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
   if (warp == 1) {
     if (lane == 0) {
       tc::mbar_init(q_full, 1);
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         tc::mbar_init(&kv_full[i], 1);
         tc::mbar_init(&kv_empty[i], 1);
-        tc::mbar_init(&s_full[i], 1);
-        tc::mbar_init(&s_empty[i], 8);
       }
-      tc::mbar_init(p_full, 8);
-      tc::mbar_init(pv_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        tc::mbar_init(&s_full[i], 1);
+        tc::mbar_init(&s_empty[i], 16);
+      }
+      tc::mbar_init(p_full, 16);
+      tc::mbar_init(&pv_full[0], 1);
+      tc::mbar_init(&pv_full[1], 1);
       tc::fence_barrier_init();
     }
     __syncwarp();
@@ -112,8 +136,18 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S0 = tmem_base, tmem_PV = tmem_base + 256, tmem_L = tmem_base + 256 + D;  // L: row sums of P
+  // The whole 512-column TMEM of the SM is allocated (one CTA per SM), so the base is column 0 / lane 0.  Using the
+  // constant keeps every TMEM address warp-uniform: with an address loaded from shared memory the compiler wrapped
+  // each tcgen05.mma of the single issuing thread in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, and with ~20 small
+  // MMAs per key tile that issue overhead was the critical path of the kernel.
+  if (*tmem_ptr_smem != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
+  // TMEM columns: S0 | S1 (128 each) | P V accumulator(s) | L = row sums of P (16 columns per buffer).
+  // D = 64: two P V buffers (256, 320) and two L buffers (384, 400); D = 128: one of each (256, 384).
+  const int nst = min(S::STAGES, p.stages);  // SS_FMHA_STAGES caps the K/V ring (A/B aid)
+  const bool kDefer = (D == 64) && p.defer;  // SS_FMHA_DEFER=0 restores the single-accumulator ordering (A/B aid)
+  const uint32_t PV_STRIDE = kDefer ? 64 : 0, L_STRIDE = kDefer ? 16 : 0;
+  const uint32_t tmem_S0 = tmem_base, tmem_PV = tmem_base + 256, tmem_L = tmem_base + 384;
 
   if (ntiles == 0) {
     // nothing visible (only possible for degenerate causal shapes): write zeros
@@ -133,8 +167,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       for (int a = 0; a < D / 64; ++a)
         tc::tma_load_2d(sQ + a * S::ATOM, &tmQ, q_full, p.q_col0 + h * p.q_col_per_head + a * 64, qrow0);
       for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int s = j % nst;
+        const uint32_t ph = (j / nst) & 1;
         tc::mbar_wait(&kv_empty[s], ph ^ 1);
         uint8_t* sK = sKV + s * 2 * S::KV_BYTES;
         uint8_t* sV = sK + S::KV_BYTES;
@@ -148,25 +182,25 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer: the whole warp runs converged, one elected lane issues =================
+    {
       constexpr uint32_t idesc_qk = tc::make_idesc(0, FT_BM, FT_BN);               // A, B K-major
       constexpr uint32_t idesc_pv = tc::make_idesc(0, FT_BM, D) | (1u << 16);      // B (V) MN-major
       const uint32_t aQ = tc::smem_u32(sQ), aP = tc::smem_u32(sP), aOnes = tc::smem_u32(sOnes);
       constexpr uint32_t idesc_l = tc::make_idesc(0, FT_BM, 16);
       auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        tc::mbar_wait(&kv_full[s], (j >> 1) & 1);
+        const int s = j % nst;
+        tc::mbar_wait(&kv_full[s], (j / nst) & 1);
         tc::mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
         tc::fence_after_sync();
         const uint32_t aK = tc::smem_u32(sKV + s * 2 * S::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * S::ATOM + (kk & 3) * 32;
-          tc::mma_f16_ss(tmem_S0 + (j & 1) * 128, tc::make_desc_sw128(aQ + off), tc::make_desc_sw128(aK + off), idesc_qk,
+          tc::mma_f16_ss_warp(tmem_S0 + (j & 1) * 128, tc::make_desc_sw128(aQ + off), tc::make_desc_sw128(aK + off), idesc_qk,
                          kk != 0);
         }
-        tc::mma_commit(&s_full[j & 1]);
+        tc::mma_commit_warp(&s_full[j & 1]);
       };
       tc::mbar_wait(q_full, 0);
       issue_qk(0);
@@ -174,62 +208,66 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
         if (j + 1 < ntiles) issue_qk(j + 1);
         tc::mbar_wait(p_full, j & 1);  // P_j is in shared memory (and PV_{j-1} has been consumed)
         tc::fence_after_sync();
-        const int s = j & 1;
+        const int s = j % nst;
         const uint32_t aV = tc::smem_u32(sKV + s * 2 * S::KV_BYTES + S::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < FT_BN / 16; ++kk) {
-          const uint64_t da = tc::make_desc_sw128(aP + (kk >> 2) * S::ATOM + (kk & 3) * 32);
+          const uint64_t da = tc::make_desc_sw128(aP + (kDefer ? (j & 1) * S::P_BYTES : 0) + (kk >> 2) * S::ATOM + (kk & 3) * 32);
           const uint64_t db = make_desc_mn_sw128(aV + kk * 16 * 128, S::ATOM);
-          tc::mma_f16_ss(tmem_PV, da, db, idesc_pv, kk != 0);
+          tc::mma_f16_ss_warp(tmem_PV + (j & 1) * PV_STRIDE, da, db, idesc_pv, kk != 0);
           // row sums of P_j by the tensor core: P (128 x 16 keys) times a 16 x 16 block of ones
-          tc::mma_f16_ss(tmem_L, da, tc::make_desc_sw128(aOnes + (kk >> 2) * 2048 + (kk & 3) * 32), idesc_l, kk != 0);
+          tc::mma_f16_ss_warp(tmem_L + (j & 1) * L_STRIDE, da, tc::make_desc_sw128(aOnes + (kk >> 2) * 2048 + (kk & 3) * 32),
+                         idesc_l, kk != 0);
         }
-        tc::mma_commit(&kv_empty[s]);  // K_j / V_j no longer needed
-        tc::mma_commit(pv_full);
+        tc::mma_commit_warp(&kv_empty[s]);  // K_j / V_j no longer needed
+        tc::mma_commit_warp(&pv_full[j & 1]);
       }
     }
   } else {
-    // ================= softmax + output: a pair of threads per query row =================
-    const int q = warp & 3;            // TMEM lane quarter
-    const int half = (warp - 2) >> 2;  // which 64 keys of the tile / which half of the output dims
+    // ================= softmax + output: FOUR threads per query row =================
+    // 16 warps (four per scheduler) hide the TMEM-load / exchange / barrier latencies of this phase far better
+    // than 8 did; warps w, w+4, w+8, w+12 see the same TMEM lane quarter and own 32 keys + D/4 output dims each.
+    const int q = warp & 3;             // TMEM lane quarter
+    const int part = (warp - 2) >> 2;   // which 32 keys of the tile / which quarter of the output dims
     const int r = q * 32 + lane;
     const int qrow = m0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    constexpr int DH = D / 2;
-    float o_acc[DH];
+    constexpr int DQ = D / 4;
+    float o_acc[DQ];
 #pragma unroll
-    for (int i = 0; i < DH; ++i) o_acc[i] = 0.f;
+    for (int i = 0; i < DQ; ++i) o_acc[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
+    const int poly = p.poly;
 
-    auto add_pv = [&]() {
+    auto add_pv = [&](int jj) {  // fold tile jj's P V product and row sums into the running output
+      tc::mbar_wait(&pv_full[jj & 1], (jj >> 1) & 1);
+      tc::fence_after_sync();
+      const uint32_t lraw = tc::tmem_ld_32x1(tmem_L + (jj & 1) * L_STRIDE + lane_off);
 #pragma unroll
-      for (int c = 0; c < DH; c += 32) {
-        uint32_t raw[32];
-        tc::tmem_ld_32x32(tmem_PV + lane_off + half * DH + c, raw);
+      for (int c = 0; c < DQ; c += 16) {  // 16 columns at a time: this runs while the 32 scores are live
+        uint32_t raw[16];
+        tc::tmem_ld_32x16(tmem_PV + (jj & 1) * PV_STRIDE + lane_off + part * DQ + c, raw);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c + i] += __uint_as_float(raw[i]);
+        for (int i = 0; i < 16; ++i) o_acc[c + i] += __uint_as_float(raw[i]);
       }
-      l_run += __uint_as_float(tc::tmem_ld_32x1(tmem_L + lane_off));
-      tc::tmem_ld_wait();
+      l_run += __uint_as_float(lraw);
     };
 
     for (int j = 0; j < ntiles; ++j) {
-      const uint32_t tS = tmem_S0 + (j & 1) * 128 + lane_off + half * 64;
-      const int key0 = j * FT_BN + half * 64;
-      const bool need_mask = (key0 + 64 > Lk) || (p.causal && (key0 + 63 > m0 + q * 32 + shift));
+      const uint32_t tS = tmem_S0 + (j & 1) * 128 + lane_off + part * 32;
+      const int key0 = j * FT_BN + part * 32;
+      const bool need_mask = (key0 + 32 > Lk) || (p.causal && (key0 + 31 > m0 + q * 32 + shift));
       const int key_lim = p.causal ? min(Lk - 1, qrow + shift) : (Lk - 1);  // last visible key for this row
       tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc::fence_after_sync();
-      // my 64 scores, read once
-      float sv[64];
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
+      float sv[32];
+      {
         uint32_t raw[32];
-        tc::tmem_ld_32x32(tS + c, raw);
+        tc::tmem_ld_32x32(tS, raw);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(raw[i]);
+        for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(raw[i]);
       }
       // S_j is in registers: the MMA warp may overwrite this buffer with S_{j+2}
       tc::fence_before_sync();
@@ -238,63 +276,72 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       float mx = -INFINITY;
       if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < 32; ++i) {
           if (key0 + i > key_lim) sv[i] = -INFINITY;
           mx = fmaxf(mx, sv[i]);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, sv[i]);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, sv[i]);
       }
-      // exchange the half-row maxima with the partner thread (same row, other 64 keys)
-      xchg[half * 128 + r] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      mx = fmaxf(fmaxf(mx, xchg[(half ^ 1) * 128 + r]), m_run);
+      // exchange the quarter-row maxima with the three partner threads (same row, other keys)
+      xchg[part * 128 + r] = mx;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(fmaxf(fmaxf(xchg[r], xchg[128 + r]), fmaxf(xchg[256 + r], xchg[384 + r])), m_run);
       const float msc = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
       const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2 - msc);
-      // fold in the previous tile's P V (computed relative to the previous maximum), then rescale
-      if (j > 0) {
-        tc::mbar_wait(pv_full, (j - 1) & 1);
-        tc::fence_after_sync();
-        add_pv();
-      }
-      if (!__all_sync(0xffffffffu, corr == 1.f)) {  // the running maximum usually settles after a few tiles
+      // fold in the previous tile's P V (computed relative to the previous maximum), then rescale.  With a
+      // single TMEM accumulator this has to happen before P_j is released (P V_j overwrites it); with two, later.
+      auto fold_prev = [&]() {
+        if (j > 0) add_pv(j - 1);
+        if (!__all_sync(0xffffffffu, corr == 1.f)) {  // the running maximum usually settles after a few tiles
 #pragma unroll
-        for (int i = 0; i < DH; ++i) o_acc[i] *= corr;
-        l_run *= corr;
-      }
+          for (int i = 0; i < DQ; ++i) o_acc[i] *= corr;
+          l_run *= corr;
+        }
+      };
+      if (!kDefer) fold_prev();
       m_run = mx;
-      // probabilities of my 64 keys -> P atom `half` (fp16, 128B-swizzled rows of 128 bytes)
-      // exp2 on packed halves (MUFU.EX2.F16x2: two results per issue); P is needed in fp16 anyway and its row
-      // sums come back from the tensor core (tmem_L), so no per-element adds are spent here
-      uint8_t* prow = sP + half * S::ATOM + r * 128;
+      // probabilities of my 32 keys -> four 16-byte pieces of P atom `part / 2` (fp16, 128B-swizzled rows of
+      // 128 bytes).  P's row sums come back from the tensor core (tmem_L), so no per-element adds are spent here.
+      uint8_t* prow = sP + (kDefer ? (j & 1) * S::P_BYTES : 0) + (part >> 1) * S::ATOM + r * 128;
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) {
+      for (int g = 0; g < 4; ++g) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float xa = fmaf(sv[g8 * 8 + 2 * i], p.scale_log2, -msc);
-          const float xb = fmaf(sv[g8 * 8 + 2 * i + 1], p.scale_log2, -msc);
-          uint32_t xh;
-          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(xb), "f"(xa));  // {hi: xb, lo: xa}
-          asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i]) : "r"(xh));
+          const float xa = fmaf(sv[g * 8 + 2 * i], p.scale_log2, -msc);
+          const float xb = fmaf(sv[g * 8 + 2 * i + 1], p.scale_log2, -msc);
+          // fp32 MUFU.EX2: the packed-half form issues as two MUFU.EX2.F16 at a lower rate (it was the top stall
+          // of this kernel in profiles/r1_ncu_fmha_softmax.md), so it bought nothing over one fp32 op per element
+          // ... `poly` of every 4 pairs take an FMA-pipe polynomial instead of the special-function unit
+          // (16 results / clk / SM), as FlashAttention-4 does on this chip; 0 = all on the MUFU
+          float ea, eb;
+          if (i < poly) {
+            ea = exp2_fma(xa);
+            eb = exp2_fma(xb);
+          } else {
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(xa));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(xb));
+          }
+          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(eb), "f"(ea));  // {hi: eb, lo: ea}
         }
-        *reinterpret_cast<uint4*>(prow + ((g8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        const int piece = (part & 1) * 4 + g;
+        *reinterpret_cast<uint4*>(prow + ((piece ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       tc::fence_proxy_async();
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // partner has read my max before I overwrite it next tile
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // partners have read my max before the next tile's
       if (lane == 0) tc::mbar_arrive(p_full);
+      if (kDefer) fold_prev();
     }
     // last tile's P V and row sums
-    tc::mbar_wait(pv_full, (ntiles - 1) & 1);
-    tc::fence_after_sync();
-    add_pv();
+    add_pv(ntiles - 1);
     const float l_tot = l_run;  // tmem_L already holds sums over all 128 keys of each tile
     if (qrow < Lq) {
       const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-      __half* orow = p.o + b * p.o_sb + (long long)qrow * p.o_sl + h * p.o_sh + half * DH;
+      __half* orow = p.o + b * p.o_sb + (long long)qrow * p.o_sl + h * p.o_sh + part * DQ;
 #pragma unroll
-      for (int c = 0; c < DH; c += 8) {
+      for (int c = 0; c < DQ; c += 8) {
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = o_acc[c + i] * inv;
@@ -366,6 +413,28 @@ int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, 
   p.q_col_per_head = (int)q_sh; p.k_col_per_head = (int)k_sh; p.v_col_per_head = (int)v_sh;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
+  {
+    static int defer = -1;
+    if (defer < 0) {
+      const char* e = getenv("SS_FMHA_DEFER");
+      defer = e ? atoi(e) : 1;
+    }
+    p.defer = defer;
+    static int stages = -1;
+    if (stages < 0) {
+      const char* e = getenv("SS_FMHA_STAGES");
+      stages = e ? atoi(e) : 4;
+      if (stages < 2) stages = 2;
+    }
+    p.stages = stages;
+    static int poly = -1;
+    if (poly < 0) {
+      const char* e = getenv("SS_FMHA_POLY");
+      poly = e ? atoi(e) : 0;
+      if (poly > 4) poly = 4;
+    }
+    p.poly = poly;
+  }
   if (D == 64) return launch_ft<64>(tq, tk, tv, p, B, stream);
   return launch_ft<128>(tq, tk, tv, p, B, stream);
 }
