@@ -5,11 +5,13 @@
 //                 each owning 64 of the tile's 128 keys and half of the output dims, so a thread reads its S slice
 //                 once (tcgen05.ld 32x32b), exchanges the row max with its partner through shared memory, and
 //                 writes its fp16 P slice (= one 128B-swizzled 64-key atom) for the next MMA
-//   PV = P V      tcgen05.mma  M=128 x N=D x K=128 with V as an MN-major B operand straight from the [key][d]
-//                 layout TMA delivers; the per-tile product is read back and folded into the fp32 running output
-//                 held in registers (O = (O + PV_{j-1}) * corr_j), so no TMEM rescale pass is needed.  With
-//                 head_dim 64 the P V / row-sum accumulators are double-buffered in TMEM, so tile j-1's product is
-//                 folded in AFTER tile j's probabilities have been handed to the tensor core (off the critical path)
+//   O += P V      tcgen05.mma  M=128 x N=D x K=128 with V as an MN-major B operand straight from the [key][d]
+//                 layout TMA delivers.  O (and the row sums L = P 1, a 16-column MMA against a block of ones)
+//                 ACCUMULATE IN TMEM across all key tiles: TMEM reads run at 64 B/clk/SM, so reading the 128x128
+//                 fp32 S tile already costs 1024 clk per tile and a per-tile read-back of P V would add 50-100 %.
+//                 The reference maximum of a row is only raised when the new tile maximum exceeds it by more
+//                 than 2^8 (exact arithmetic is unchanged: P and L use the same reference); only then is the
+//                 accumulator read, rescaled and written back — rare after the first tiles.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = softmax + output.
 // Same mask semantics as fmha.cu: causal diagonal anchored bottom-right (xformers LowerTriangularFromBottomRightMask,
 // modeling_llama_xformer.py:289-295), keys >= Lk masked.  Operands are row-matrix views (token rows, heads side by
@@ -32,7 +34,7 @@ struct FtParams {
   int q_col0, k_col0, v_col0;
   float scale_log2;
   int causal;
-  int defer, stages, poly;
+  int stages, poly;
 };
 
 // 2^x for x <= 0 on the FMA / integer pipes: round-to-nearest split x = xi + xf (magic-number add), a degree-3
@@ -54,7 +56,7 @@ struct FtSmem {
   static constexpr int ATOM = 128 * 128;            // [128 rows][64 x 16-bit] = 16 KB
   static constexpr int Q_BYTES = (D / 64) * ATOM;
   static constexpr int KV_BYTES = (D / 64) * ATOM;  // K tile or V tile
-  static constexpr int P_BYTES = 2 * ATOM;          // one P tile; D = 64 keeps two (see kDefer)
+  static constexpr int P_BYTES = 2 * ATOM;          // one P tile; D = 64 has the shared memory for two
   static constexpr int P_BUFS = (D == 64) ? 2 : 1;
   // K/V stages: a tile's K/V can only be requested once the P V product two (STAGES) tiles back has retired, so two
   // stages leave the TMA latency exposed on every tile; head_dim 64 has the shared memory for four
@@ -142,12 +144,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
   // MMAs per key tile that issue overhead was the critical path of the kernel.
   if (*tmem_ptr_smem != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
-  // TMEM columns: S0 | S1 (128 each) | P V accumulator(s) | L = row sums of P (16 columns per buffer).
-  // D = 64: two P V buffers (256, 320) and two L buffers (384, 400); D = 128: one of each (256, 384).
+  // TMEM columns: S0 | S1 (128 each) | O accumulator (D columns at 256) | L = row sums of P (16 columns at 384)
   const int nst = min(S::STAGES, p.stages);  // SS_FMHA_STAGES caps the K/V ring (A/B aid)
-  const bool kDefer = (D == 64) && p.defer;  // SS_FMHA_DEFER=0 restores the single-accumulator ordering (A/B aid)
-  const uint32_t PV_STRIDE = kDefer ? 64 : 0, L_STRIDE = kDefer ? 16 : 0;
-  const uint32_t tmem_S0 = tmem_base, tmem_PV = tmem_base + 256, tmem_L = tmem_base + 384;
+  constexpr int PB = S::P_BUFS;
+  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 256, tmem_L = tmem_base + 384;
 
   if (ntiles == 0) {
     // nothing visible (only possible for degenerate causal shapes): write zeros
@@ -205,19 +205,19 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       tc::mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) issue_qk(j + 1);
-        tc::mbar_wait(p_full, j & 1);  // P_j is in shared memory (and PV_{j-1} has been consumed)
+        if (j + 1 < ntiles) issue_qk(j + 1);  // S_{j+1} is computed while the softmax works on S_j
+        tc::mbar_wait(p_full, j & 1);  // P_j is in shared memory
         tc::fence_after_sync();
         const int s = j % nst;
         const uint32_t aV = tc::smem_u32(sKV + s * 2 * S::KV_BYTES + S::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < FT_BN / 16; ++kk) {
-          const uint64_t da = tc::make_desc_sw128(aP + (kDefer ? (j & 1) * S::P_BYTES : 0) + (kk >> 2) * S::ATOM + (kk & 3) * 32);
+          const uint64_t da = tc::make_desc_sw128(aP + (j % PB) * S::P_BYTES + (kk >> 2) * S::ATOM + (kk & 3) * 32);
           const uint64_t db = make_desc_mn_sw128(aV + kk * 16 * 128, S::ATOM);
-          tc::mma_f16_ss_warp(tmem_PV + (j & 1) * PV_STRIDE, da, db, idesc_pv, kk != 0);
+          tc::mma_f16_ss_warp(tmem_O, da, db, idesc_pv, (j | kk) != 0);
           // row sums of P_j by the tensor core: P (128 x 16 keys) times a 16 x 16 block of ones
-          tc::mma_f16_ss_warp(tmem_L + (j & 1) * L_STRIDE, da, tc::make_desc_sw128(aOnes + (kk >> 2) * 2048 + (kk & 3) * 32),
-                         idesc_l, kk != 0);
+          tc::mma_f16_ss_warp(tmem_L, da, tc::make_desc_sw128(aOnes + (kk >> 2) * 2048 + (kk & 3) * 32), idesc_l,
+                              (j | kk) != 0);
         }
         tc::mma_commit_warp(&kv_empty[s]);  // K_j / V_j no longer needed
         tc::mma_commit_warp(&pv_full[j & 1]);
@@ -233,42 +233,26 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
     const int qrow = m0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     constexpr int DQ = D / 4;
-    float o_acc[DQ];
-#pragma unroll
-    for (int i = 0; i < DQ; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_ref = -INFINITY;  // reference maximum of this row (raw score units), shared by its four threads
     const int poly = p.poly;
-
-    auto add_pv = [&](int jj) {  // fold tile jj's P V product and row sums into the running output
+    const float raise_thresh = 8.f / p.scale_log2;  // raise the reference only for a > 2^8 jump
+    // every P V product issued so far has retired (commits are cumulative)
+    auto wait_pv = [&](int jj) {
       tc::mbar_wait(&pv_full[jj & 1], (jj >> 1) & 1);
       tc::fence_after_sync();
-      const uint32_t lraw = tc::tmem_ld_32x1(tmem_L + (jj & 1) * L_STRIDE + lane_off);
-#pragma unroll
-      for (int c = 0; c < DQ; c += 16) {  // 16 columns at a time: this runs while the 32 scores are live
-        uint32_t raw[16];
-        tc::tmem_ld_32x16(tmem_PV + (jj & 1) * PV_STRIDE + lane_off + part * DQ + c, raw);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[c + i] += __uint_as_float(raw[i]);
-      }
-      l_run += __uint_as_float(lraw);
     };
 
+    const uint32_t tS0 = tmem_S0 + lane_off + part * 32;
+
     for (int j = 0; j < ntiles; ++j) {
-      const uint32_t tS = tmem_S0 + (j & 1) * 128 + lane_off + part * 32;
       const int key0 = j * FT_BN + part * 32;
       const bool need_mask = (key0 + 32 > Lk) || (p.causal && (key0 + 31 > m0 + q * 32 + shift));
       const int key_lim = p.causal ? min(Lk - 1, qrow + shift) : (Lk - 1);  // last visible key for this row
       tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc::fence_after_sync();
-      float sv[32];
-      {
-        uint32_t raw[32];
-        tc::tmem_ld_32x32(tS, raw);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(raw[i]);
-      }
+      uint32_t cur[32];  // my 32 scores (fp32 bits), read once
+      tc::tmem_ld_32x32(tS0 + (j & 1) * 128, cur);
+      tc::tmem_ld_wait();
       // S_j is in registers: the MMA warp may overwrite this buffer with S_{j+2}
       tc::fence_before_sync();
       __syncwarp();
@@ -277,45 +261,63 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       if (need_mask) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (key0 + i > key_lim) sv[i] = -INFINITY;
-          mx = fmaxf(mx, sv[i]);
+          if (key0 + i > key_lim) cur[i] = 0xff800000u;  // -inf
+          mx = fmaxf(mx, __uint_as_float(cur[i]));
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, sv[i]);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
       }
       // exchange the quarter-row maxima with the three partner threads (same row, other keys)
       xchg[part * 128 + r] = mx;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
-      mx = fmaxf(fmaxf(fmaxf(xchg[r], xchg[128 + r]), fmaxf(xchg[256 + r], xchg[384 + r])), m_run);
-      const float msc = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
-      const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2 - msc);
-      // fold in the previous tile's P V (computed relative to the previous maximum), then rescale.  With a
-      // single TMEM accumulator this has to happen before P_j is released (P V_j overwrites it); with two, later.
-      auto fold_prev = [&]() {
-        if (j > 0) add_pv(j - 1);
-        if (!__all_sync(0xffffffffu, corr == 1.f)) {  // the running maximum usually settles after a few tiles
+      mx = fmaxf(fmaxf(xchg[r], xchg[128 + r]), fmaxf(xchg[256 + r], xchg[384 + r]));
+      if (j == 0) {
+        m_ref = mx;  // O_0 = P_0 V_0 overwrites the accumulator: nothing to rescale
+      } else {
+        const bool raise = mx > m_ref + raise_thresh;  // also true when m_ref is still -inf and mx is finite
+        if (__any_sync(0xffffffffu, raise)) {
+          // rare after the first tiles: bring this warp's 32 rows x D/4 output dims (and 4 of the 16 row-sum
+          // columns) to the new reference.  All four partner warps take the same decision (same row maxima).
+          const float corr = raise ? exp2f((m_ref - mx) * p.scale_log2) : 1.f;
+          if (raise) m_ref = mx;
+          wait_pv(j - 1);
 #pragma unroll
-          for (int i = 0; i < DQ; ++i) o_acc[i] *= corr;
-          l_run *= corr;
+          for (int c = 0; c < DQ; c += 16) {
+            uint32_t raw[16];
+            tc::tmem_ld_32x16(tmem_O + lane_off + part * DQ + c, raw);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+            tc::tmem_st_32x16(tmem_O + lane_off + part * DQ + c, raw);
+          }
+          {
+            uint32_t raw[4];
+            tc::tmem_ld_32x4(tmem_L + lane_off + part * 4, raw);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+            tc::tmem_st_32x4(tmem_L + lane_off + part * 4, raw);
+          }
+          tc::tmem_st_wait();
+          tc::fence_before_sync();  // ordered before the p_full arrival that releases P V_j
         }
-      };
-      if (!kDefer) fold_prev();
-      m_run = mx;
+      }
+      const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
+      // the P buffer about to be overwritten was last read by P V_{j-PB}
+      if (j >= PB) wait_pv(j - PB);
       // probabilities of my 32 keys -> four 16-byte pieces of P atom `part / 2` (fp16, 128B-swizzled rows of
-      // 128 bytes).  P's row sums come back from the tensor core (tmem_L), so no per-element adds are spent here.
-      uint8_t* prow = sP + (kDefer ? (j & 1) * S::P_BYTES : 0) + (part >> 1) * S::ATOM + r * 128;
+      // 128 bytes).  P's row sums come from the tensor core (tmem_L), so no per-element adds are spent here.
+      uint8_t* prow = sP + (j % PB) * S::P_BYTES + (part >> 1) * S::ATOM + r * 128;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float xa = fmaf(sv[g * 8 + 2 * i], p.scale_log2, -msc);
-          const float xb = fmaf(sv[g * 8 + 2 * i + 1], p.scale_log2, -msc);
-          // fp32 MUFU.EX2: the packed-half form issues as two MUFU.EX2.F16 at a lower rate (it was the top stall
-          // of this kernel in profiles/r1_ncu_fmha_softmax.md), so it bought nothing over one fp32 op per element
-          // ... `poly` of every 4 pairs take an FMA-pipe polynomial instead of the special-function unit
-          // (16 results / clk / SM), as FlashAttention-4 does on this chip; 0 = all on the MUFU
+          const float xa = fmaf(__uint_as_float(cur[g * 8 + 2 * i]), p.scale_log2, -msc);
+          const float xb = fmaf(__uint_as_float(cur[g * 8 + 2 * i + 1]), p.scale_log2, -msc);
+          // fp32 MUFU.EX2 (the packed-half form issues as two MUFU.EX2.F16 and is no faster); `poly` of every
+          // 4 pairs may take an FMA-pipe polynomial instead (SS_FMHA_POLY, 0 = all on the special-function unit)
           float ea, eb;
           if (i < poly) {
             ea = exp2_fma(xa);
@@ -332,20 +334,25 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
       tc::fence_proxy_async();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // partners have read my max before the next tile's
       if (lane == 0) tc::mbar_arrive(p_full);
-      if (kDefer) fold_prev();
     }
-    // last tile's P V and row sums
-    add_pv(ntiles - 1);
-    const float l_tot = l_run;  // tmem_L already holds sums over all 128 keys of each tile
-    if (qrow < Lq) {
+    // all products retired: read the accumulator once, normalise, store
+    wait_pv(ntiles - 1);
+    const float l_tot = __uint_as_float(tc::tmem_ld_32x1(tmem_L + lane_off));
+    __half* orow = p.o + b * p.o_sb + (long long)qrow * p.o_sl + h * p.o_sh + part * DQ;
+#pragma unroll
+    for (int c = 0; c < DQ; c += 16) {
+      uint32_t raw[16];
+      tc::tmem_ld_32x16(tmem_O + lane_off + part * DQ + c, raw);
+      tc::tmem_ld_wait();
       const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-      __half* orow = p.o + b * p.o_sb + (long long)qrow * p.o_sl + h * p.o_sh + part * DQ;
+      if (qrow < Lq) {
 #pragma unroll
-      for (int c = 0; c < DQ; c += 8) {
-        float f[8];
+        for (int c8 = 0; c8 < 16; c8 += 8) {
+          float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = o_acc[c + i] * inv;
-        *reinterpret_cast<vec8*>(orow + c) = pack8<__half>(f);
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(raw[c8 + i]) * inv;
+          *reinterpret_cast<vec8*>(orow + c + c8) = pack8<__half>(f);
+        }
       }
     }
   }
@@ -414,12 +421,6 @@ int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, 
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   {
-    static int defer = -1;
-    if (defer < 0) {
-      const char* e = getenv("SS_FMHA_DEFER");
-      defer = e ? atoi(e) : 1;
-    }
-    p.defer = defer;
     static int stages = -1;
     if (stages < 0) {
       const char* e = getenv("SS_FMHA_STAGES");
