@@ -62,7 +62,8 @@ struct FtSmem {
   // stages leave the TMA latency exposed on every tile; head_dim 64 has the shared memory for four
   static constexpr int STAGES = (D == 64) ? 4 : 2;
   static constexpr int ONES_BYTES = 4096;           // [16][128] fp16 ones: B operand of the row-sum MMA
-  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BUFS * P_BYTES + ONES_BYTES + 1024 + 256 + 2048 /*row-max exchange*/;
+  static constexpr int TOTAL = Q_BYTES + STAGES * 2 * KV_BYTES + P_BUFS * P_BYTES + ONES_BYTES + 1024 + 256 + 2048 /*row-max exchange*/ +
+                               1024 /*final per-group maxima (ping-pong kernel)*/;
 };
 
 // MN-major B operand (V as [key][d] rows of 128 bytes, 128B swizzle): SBO = 8 key rows * 128 B, LBO = distance between
@@ -362,6 +363,287 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
+
+// =============================================================================================
+// head_dim 64, "ping-pong" variant: the 16 softmax warps form TWO independent groups.  Group g owns the key tiles
+// j = g (mod 2) together with S buffer g, P buffer g and its own O_g / L_g accumulators in TMEM, and keeps its own
+// reference maximum; the two partial results are merged once at the end (as a split-KV decode would).  While one
+// group reads its S tile out of TMEM (64 B/clk/SM) the other is on the special-function unit, and neither waits
+// for the other's P V product — in the single-group kernel those phases ran in lockstep across all 16 warps.
+// A group is 8 warps = 2 threads per query row (64 keys + 32 output dims each).
+// TMEM columns: S_0 | S_1 (128 each) | O_0 (256) | O_1 (320) | L_0 (384) | L_1 (400).
+// =============================================================================================
+__global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_pp_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV,
+                                                                   const FtParams p) {
+  constexpr int D = 64;
+  using S = FtSmem<D>;
+  extern __shared__ uint8_t ft_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + S::Q_BYTES;  // stage s: K at s*2*KV, V right after
+  uint8_t* sP = sKV + S::STAGES * 2 * S::KV_BYTES;
+  uint8_t* sOnes = sP + S::P_BUFS * S::P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + S::ONES_BYTES);
+  uint64_t* q_full = bars;        // 1
+  uint64_t* kv_full = bars + 1;   // [4]
+  uint64_t* kv_empty = bars + 5;  // [4]
+  uint64_t* s_full = bars + 9;    // [2] one per group
+  uint64_t* s_empty = bars + 11;  // [2]
+  uint64_t* p_full = bars + 13;   // [2]
+  uint64_t* pv_full = bars + 15;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
+  float* xchg = reinterpret_cast<float*>(bars + 20);  // [2 groups][2 halves][128 rows] row-max exchange
+  float* mfin = xchg + 512;                           // [2 groups][128 rows] final reference maxima
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * FT_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int Lq = p.Lq, Lk = p.Lk;
+  const int shift = Lk - Lq;
+  int n_end = Lk;
+  if (p.causal) n_end = min(Lk, m0 + FT_BM + shift);
+  const int ntiles = (n_end + FT_BN - 1) / FT_BN;
+  const int nst = min(S::STAGES, p.stages);
+
+  for (int i = threadIdx.x; i < S::ONES_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3C003C00u;
+  tc::fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmQ);
+    tc::prefetch_tmap(&tmK);
+    tc::prefetch_tmap(&tmV);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      tc::mbar_init(q_full, 1);
+      for (int i = 0; i < 4; ++i) {
+        tc::mbar_init(&kv_full[i], 1);
+        tc::mbar_init(&kv_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        tc::mbar_init(&s_full[i], 1);
+        tc::mbar_init(&s_empty[i], 8);
+        tc::mbar_init(&p_full[i], 8);
+        tc::mbar_init(&pv_full[i], 1);
+      }
+      tc::fence_barrier_init();
+    }
+    __syncwarp();
+    tc::tmem_alloc(tmem_ptr_smem, 512);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (*tmem_ptr_smem != 0u) __trap();  // all 512 columns are ours: base 0 keeps every TMEM address warp-uniform
+  constexpr uint32_t tmem_S0 = 0u, tmem_O = 256u, tmem_L = 384u;
+
+  if (ntiles == 0) {
+    if (warp >= 2 && warp < 6) {
+      const int r = (warp & 3) * 32 + lane;
+      if (m0 + r < Lq) {
+        __half* orow = p.o + b * p.o_sb + (long long)(m0 + r) * p.o_sl + h * p.o_sh;
+        for (int d = 0; d < D; ++d) orow[d] = __float2half_rn(0.f);
+      }
+    }
+  } else if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int qrow0 = b * p.q_rows_per_batch + m0;
+      tc::mbar_expect_tx(q_full, S::Q_BYTES);
+      tc::tma_load_2d(sQ, &tmQ, q_full, p.q_col0 + h * p.q_col_per_head, qrow0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % nst;
+        tc::mbar_wait(&kv_empty[s], ((j / nst) & 1) ^ 1);
+        uint8_t* sK = sKV + s * 2 * S::KV_BYTES;
+        uint8_t* sV = sK + S::KV_BYTES;
+        const int krow0 = b * p.k_rows_per_batch + j * FT_BN;
+        tc::mbar_expect_tx(&kv_full[s], 2 * S::KV_BYTES);
+        tc::tma_load_2d(sK, &tmK, &kv_full[s], p.k_col0 + h * p.k_col_per_head, krow0);
+        tc::tma_load_2d(sV, &tmV, &kv_full[s], p.v_col0 + h * p.v_col_per_head, krow0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: the whole warp runs converged, one elected lane issues =================
+    constexpr uint32_t idesc_qk = tc::make_idesc(0, FT_BM, FT_BN);           // A, B K-major
+    constexpr uint32_t idesc_pv = tc::make_idesc(0, FT_BM, D) | (1u << 16);  // B (V) MN-major
+    constexpr uint32_t idesc_l = tc::make_idesc(0, FT_BM, 16);
+    const uint32_t aQ = tc::smem_u32(sQ), aP = tc::smem_u32(sP), aOnes = tc::smem_u32(sOnes);
+    auto issue_qk = [&](int j) {
+      const int s = j % nst;
+      tc::mbar_wait(&kv_full[s], (j / nst) & 1);
+      tc::mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+      tc::fence_after_sync();
+      const uint32_t aK = tc::smem_u32(sKV + s * 2 * S::KV_BYTES);
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk)
+        tc::mma_f16_ss_warp(tmem_S0 + (j & 1) * 128, tc::make_desc_sw128(aQ + kk * 32), tc::make_desc_sw128(aK + kk * 32),
+                            idesc_qk, kk != 0);
+      tc::mma_commit_warp(&s_full[j & 1]);
+    };
+    tc::mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < ntiles; ++j) {
+      if (j + 1 < ntiles) issue_qk(j + 1);
+      const int g = j & 1;
+      tc::mbar_wait(&p_full[g], (j >> 1) & 1);  // P_j (group g) is in shared memory
+      tc::fence_after_sync();
+      const int s = j % nst;
+      const uint32_t aV = tc::smem_u32(sKV + s * 2 * S::KV_BYTES + S::KV_BYTES);
+      const uint32_t acc0 = j >= 2;  // the group's first tile overwrites its accumulators
+#pragma unroll
+      for (int kk = 0; kk < FT_BN / 16; ++kk) {
+        const uint64_t da = tc::make_desc_sw128(aP + g * S::P_BYTES + (kk >> 2) * S::ATOM + (kk & 3) * 32);
+        const uint64_t db = make_desc_mn_sw128(aV + kk * 16 * 128, S::ATOM);
+        tc::mma_f16_ss_warp(tmem_O + g * 64, da, db, idesc_pv, acc0 | (kk != 0));
+        tc::mma_f16_ss_warp(tmem_L + g * 16, da, tc::make_desc_sw128(aOnes + (kk >> 2) * 2048 + (kk & 3) * 32), idesc_l,
+                            acc0 | (kk != 0));
+      }
+      tc::mma_commit_warp(&kv_empty[s]);  // K_j / V_j no longer needed
+      tc::mma_commit_warp(&pv_full[g]);
+    }
+  } else {
+    // ================= softmax: two groups of 8 warps, a pair of threads per query row in each =================
+    const int q = warp & 3;              // TMEM lane quarter
+    const int idx = (warp - 2) >> 2;     // 0..3
+    const int g = idx & 1;               // group = parity of the key tiles it owns
+    const int half = idx >> 1;           // which 64 keys of the tile / which half of the output dims
+    const int r = q * 32 + lane;
+    const int qrow = m0 + r;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int bar_pair = 1 + g * 4 + q;  // named barrier of the 64 threads sharing (group, lane quarter)
+    float m_ref = -INFINITY;
+    const float raise_thresh = 8.f / p.scale_log2;
+    float* xg = xchg + g * 256;
+    auto wait_pv = [&](int t) {  // the group's t-th P V product (and everything before it) has retired
+      tc::mbar_wait(&pv_full[g], t & 1);
+      tc::fence_after_sync();
+    };
+
+    int t = 0;
+    for (int j = g; j < ntiles; j += 2, ++t) {
+      const uint32_t tS = tmem_S0 + g * 128 + lane_off + half * 64;
+      const int key0 = j * FT_BN + half * 64;
+      const bool need_mask = (key0 + 64 > Lk) || (p.causal && (key0 + 63 > m0 + q * 32 + shift));
+      const int key_lim = p.causal ? min(Lk - 1, qrow + shift) : (Lk - 1);
+      tc::mbar_wait(&s_full[g], t & 1);
+      tc::fence_after_sync();
+      uint32_t cur[64];  // my 64 scores (fp32 bits), read once
+      tc::tmem_ld_32x32(tS, cur);
+      tc::tmem_ld_32x32(tS + 32, cur + 32);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s_empty[g]);  // the MMA warp may overwrite S_g with the group's next tile
+      float mx = -INFINITY;
+      if (need_mask) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          if (key0 + i > key_lim) cur[i] = 0xff800000u;  // -inf
+          mx = fmaxf(mx, __uint_as_float(cur[i]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+      }
+      xg[half * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_pair) : "memory");
+      mx = fmaxf(mx, xg[(half ^ 1) * 128 + r]);
+      if (t == 0) {
+        m_ref = mx;
+      } else {
+        const bool raise = mx > m_ref + raise_thresh;
+        if (__any_sync(0xffffffffu, raise)) {
+          const float corr = raise ? exp2f((m_ref - mx) * p.scale_log2) : 1.f;
+          if (raise) m_ref = mx;
+          wait_pv(t - 1);
+#pragma unroll
+          for (int c = 0; c < 32; c += 16) {
+            uint32_t raw[16];
+            tc::tmem_ld_32x16(tmem_O + g * 64 + lane_off + half * 32 + c, raw);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+            tc::tmem_st_32x16(tmem_O + g * 64 + lane_off + half * 32 + c, raw);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; c += 4) {
+            uint32_t raw[4];
+            tc::tmem_ld_32x4(tmem_L + g * 16 + lane_off + half * 8 + c, raw);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+            tc::tmem_st_32x4(tmem_L + g * 16 + lane_off + half * 8 + c, raw);
+          }
+          tc::tmem_st_wait();
+          tc::fence_before_sync();
+        }
+      }
+      const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
+      if (t >= 1) wait_pv(t - 1);  // P_g was last read by the group's previous P V product
+      uint8_t* prow = sP + g * S::P_BYTES + half * S::ATOM + r * 128;
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xa = fmaf(__uint_as_float(cur[g8 * 8 + 2 * i]), p.scale_log2, -msc);
+          const float xb = fmaf(__uint_as_float(cur[g8 * 8 + 2 * i + 1]), p.scale_log2, -msc);
+          float ea, eb;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(xa));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(xb));
+          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(eb), "f"(ea));  // {hi: eb, lo: ea}
+        }
+        *reinterpret_cast<uint4*>(prow + ((g8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      tc::fence_proxy_async();
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_pair) : "memory");  // partner has read my max before the next tile's
+      if (lane == 0) tc::mbar_arrive(&p_full[g]);
+    }
+    // ---- merge the two groups' partial results ----
+    // the last product overall has retired => so has every earlier one of either group (commits are cumulative)
+    tc::mbar_wait(&pv_full[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+    tc::fence_after_sync();
+    if (half == 0) mfin[g * 128 + r] = m_ref;
+    asm volatile("bar.sync %0, 128;" ::"r"(9 + q) : "memory");
+    const bool has_b = ntiles >= 2;  // group 1 owns no tile when there is a single key tile (its TMEM is undefined)
+    const float mA = mfin[r], mB = has_b ? mfin[128 + r] : -INFINITY;
+    const float mm = fmaxf(mA, mB);
+    const float wA = (mA == -INFINITY) ? 0.f : exp2f((mA - mm) * p.scale_log2);
+    const float wB = (mB == -INFINITY) ? 0.f : exp2f((mB - mm) * p.scale_log2);
+    const int d0 = half * 32 + g * 16;  // this thread's 16 output dims
+    uint32_t oa[16], ob[16];
+    tc::tmem_ld_32x16(tmem_O + lane_off + d0, oa);
+    float l_tot = __uint_as_float(tc::tmem_ld_32x1(tmem_L + lane_off)) * wA;
+    if (has_b) {
+      tc::tmem_ld_32x16(tmem_O + 64 + lane_off + d0, ob);
+      const float lb = __uint_as_float(tc::tmem_ld_32x1(tmem_L + 16 + lane_off));
+      tc::tmem_ld_wait();
+      l_tot += lb * wB;
+    } else {
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) ob[i] = 0u;
+    }
+    if (qrow < Lq) {
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      __half* orow = p.o + b * p.o_sb + (long long)qrow * p.o_sl + h * p.o_sh + d0;
+#pragma unroll
+      for (int c8 = 0; c8 < 16; c8 += 8) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          f[i] = (__uint_as_float(oa[c8 + i]) * wA + __uint_as_float(ob[c8 + i]) * wB) * inv;
+        *reinterpret_cast<vec8*>(orow + c8) = pack8<__half>(f);
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(0u, 512);
+}
+
 // tensor-map helper (defined in gemm_tc.cu)
 }  // namespace
 
@@ -379,6 +661,19 @@ int launch_ft(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& t
     attr = true;
   }
   dim3 grid((p.Lq + FT_BM - 1) / FT_BM, p.H, B);
+  if constexpr (D == 64) {
+    static int pingpong = -1;
+    if (pingpong < 0) {
+      const char* e = getenv("SS_FMHA_PINGPONG");
+      pingpong = e ? atoi(e) : 1;
+      SS_CUDA(cudaFuncSetAttribute(fmha_tc_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    }
+    if (pingpong) {
+      fmha_tc_pp_kernel<<<grid, FT_THREADS, S::TOTAL, s>>>(tq, tk, tv, p);
+      SS_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   fmha_tc_kernel<D><<<grid, FT_THREADS, S::TOTAL, s>>>(tq, tk, tv, p);
   SS_LAUNCH_CHECK();
   return 0;
