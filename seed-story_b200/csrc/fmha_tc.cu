@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_pp_kernel(const __grid_
     constexpr uint32_t idesc_qk = tc::make_idesc(0, FT_BM, FT_BN);           // A, B K-major
     constexpr uint32_t idesc_pv = tc::make_idesc(0, FT_BM, D) | (1u << 16);  // B (V) MN-major
     constexpr uint32_t idesc_l = tc::make_idesc(0, FT_BM, 16);
-    const uint32_t aQ = tc::smem_u32(sQ), aP = tc::smem_u32(sP), aOnes = tc::smem_u32(sOnes);
+    const uint32_t aQ = tc::smem_u32(sQ), aOnes = tc::smem_u32(sOnes);
     auto issue_qk = [&](int j) {
       const int s = j % nst;
       tc::mbar_wait(&kv_full[s], (j / nst) & 1);
@@ -491,12 +491,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_pp_kernel(const __grid_
       const int s = j % nst;
       const uint32_t aV = tc::smem_u32(sKV + s * 2 * S::KV_BYTES + S::KV_BYTES);
       const uint32_t acc0 = j >= 2;  // the group's first tile overwrites its accumulators
+      // A = P_j straight from TMEM (the first 64 columns of S_g, 16 keys = 8 columns per MMA): P never touches
+      // shared memory, which was the busiest resource of the kernel (P written once and read twice per tile)
 #pragma unroll
       for (int kk = 0; kk < FT_BN / 16; ++kk) {
-        const uint64_t da = tc::make_desc_sw128(aP + g * S::P_BYTES + (kk >> 2) * S::ATOM + (kk & 3) * 32);
+        const uint32_t ta = tmem_S0 + g * 128 + kk * 8;
         const uint64_t db = make_desc_mn_sw128(aV + kk * 16 * 128, S::ATOM);
-        tc::mma_f16_ss_warp(tmem_O + g * 64, da, db, idesc_pv, acc0 | (kk != 0));
-        tc::mma_f16_ss_warp(tmem_L + g * 16, da, tc::make_desc_sw128(aOnes + (kk >> 2) * 2048 + (kk & 3) * 32), idesc_l,
+        tc::mma_f16_ts_warp(tmem_O + g * 64, ta, db, idesc_pv, acc0 | (kk != 0));
+        tc::mma_f16_ts_warp(tmem_L + g * 16, ta, tc::make_desc_sw128(aOnes + (kk >> 2) * 2048 + (kk & 3) * 32), idesc_l,
                             acc0 | (kk != 0));
       }
       tc::mma_commit_warp(&kv_empty[s]);  // K_j / V_j no longer needed
@@ -580,23 +582,22 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_pp_kernel(const __grid_
         }
       }
       const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
-      if (t >= 1) wait_pv(t - 1);  // P_g was last read by the group's previous P V product
-      uint8_t* prow = sP + g * S::P_BYTES + half * S::ATOM + r * 128;
+      // P_j (fp16 pairs, key 2c in the low half of column c) overwrites the first 64 columns of S_g: my 64 keys are
+      // columns half*32 .. +31.  Both threads of the row hold their scores in registers (the exchange barrier above),
+      // and the tensor pipe is in order, so the group's next Q K^T cannot overtake the P V that reads this.
+      uint32_t pk[32];
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float xa = fmaf(__uint_as_float(cur[g8 * 8 + 2 * i]), p.scale_log2, -msc);
-          const float xb = fmaf(__uint_as_float(cur[g8 * 8 + 2 * i + 1]), p.scale_log2, -msc);
-          float ea, eb;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(xa));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(xb));
-          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(eb), "f"(ea));  // {hi: eb, lo: ea}
-        }
-        *reinterpret_cast<uint4*>(prow + ((g8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      for (int i = 0; i < 32; ++i) {
+        const float xa = fmaf(__uint_as_float(cur[2 * i]), p.scale_log2, -msc);
+        const float xb = fmaf(__uint_as_float(cur[2 * i + 1]), p.scale_log2, -msc);
+        float ea, eb;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(xa));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(xb));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(eb), "f"(ea));  // {hi: eb, lo: ea}
       }
-      tc::fence_proxy_async();
+      tc::tmem_st_32x32(tmem_S0 + g * 128 + lane_off + half * 32, pk);
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
       asm volatile("bar.sync %0, 64;" ::"r"(bar_pair) : "memory");  // partner has read my max before the next tile's
       if (lane == 0) tc::mbar_arrive(&p_full[g]);
     }

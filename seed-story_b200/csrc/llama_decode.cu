@@ -265,26 +265,40 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
   const int sub = lane >> 4, l16 = lane & 15;
   float qf[8];
   unpack8<__half>(*reinterpret_cast<const vec8*>(qs + l16 * 8), qf);
-  const int* pt = page_table + (size_t)b * max_pages;
+  // the split's page ids (<= 16) are staged once: the per-token lookup is then a shared-memory read instead of a
+  // dependent global load in front of every K / V row
+  __shared__ int pg[AD_MAX_CHUNK / KV_PAGE];
+  if (threadIdx.x < p1 - p0) pg[threadIdx.x] = page_table[(size_t)b * max_pages + p0 + threadIdx.x];
+  __syncthreads();
   float lmax = -INFINITY;
-  // warp-uniform trip count: the half-warp shuffles below need all 32 lanes converged
-  for (int j0 = warp * 2; j0 < cnt; j0 += (AD_THREADS / 32) * 2) {
-    const int j = j0 + sub;
-    const bool valid = j < cnt;
-    const int tok = t0 + (valid ? j : 0);
-    const int page = pt[tok / KV_PAGE];
-    const __half* kr = kcache + (((size_t)page * H + h) * KV_PAGE + (tok % KV_PAGE)) * D + l16 * 8;
-    float kf[8];
-    unpack8<__half>(ld_cached16(kr), kf);
-    float d = 0.f;
+  // warp-uniform trip count (the half-warp shuffles need all 32 lanes converged); four passes of 8 tokens are
+  // batched so that every lane has four independent 16-byte K loads in flight — with one load per pass the loop
+  // paid a full HBM latency per 8 tokens (20 us per layer at ctx 1041 against 2.6 us of traffic)
+  constexpr int PASS = (AD_THREADS / 32) * 2;
+  for (int jb = warp * 2; jb < cnt; jb += PASS * 4) {
+    vec8 kv[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d += qf[i] * kf[i];
+    for (int u = 0; u < 4; ++u) {
+      const int j = jb + u * PASS + sub;
+      const int jj = j < cnt ? j : 0;
+      const int page = pg[jj / KV_PAGE];  // t0 is page aligned
+      kv[u] = ld_stream16(kcache + (((size_t)page * H + h) * KV_PAGE + (jj % KV_PAGE)) * D + l16 * 8);
+    }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    d *= scale;
-    if (valid) {
-      if (l16 == 0) sc[j] = d;
-      lmax = fmaxf(lmax, d);
+    for (int u = 0; u < 4; ++u) {
+      const int j = jb + u * PASS + sub;
+      float kf[8];
+      unpack8<__half>(kv[u], kf);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d += qf[i] * kf[i];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      d *= scale;
+      if (j < cnt) {
+        if (l16 == 0) sc[j] = d;
+        lmax = fmaxf(lmax, d);
+      }
     }
   }
   const float m = block_max(lmax, red);
@@ -304,10 +318,9 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll 4
   for (int j = warp * 2 + sub; j < cnt; j += (AD_THREADS / 32) * 2) {
-    const int tok = t0 + j;
-    const int page = pt[tok / KV_PAGE];
+    const int page = pg[j / KV_PAGE];
     float vf[8];
-    unpack8<__half>(ld_cached16(vcache + (((size_t)page * H + h) * KV_PAGE + (tok % KV_PAGE)) * D + l16 * 8), vf);
+    unpack8<__half>(ld_stream16(vcache + (((size_t)page * H + h) * KV_PAGE + (j % KV_PAGE)) * D + l16 * 8), vf);
     const float pj = sc[j];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += pj * vf[i];

@@ -43,7 +43,7 @@ def rope_tables_f16(head_dim, n_pos, device, base=10000.0):
 
 
 class LlamaEngine:
-    def __init__(self, cfg, device, max_batch=1, max_ctx=4096, max_new=512, decode_splits=16):
+    def __init__(self, cfg, device, max_batch=1, max_ctx=4096, max_new=512, decode_splits=32):
         ops.require_device()
         self.cfg, self.dev = cfg, device
         self.max_batch = max_batch

@@ -354,7 +354,7 @@ class VAEDecoderEngine:
             self.up.append((res, up))
         self.norm_out = (g("decoder.conv_norm_out.weight"), g("decoder.conv_norm_out.bias"))
         self.conv_out = (_pack_conv3(g("decoder.conv_out.weight"), cout_pad=8), _pad_vec(g("decoder.conv_out.bias"), 8))
-        self.gn_ws = torch.zeros(2 * self.groups * 1024, dtype=torch.float32, device=device)
+        self.gn_ws = torch.zeros(2 * self.groups * 2048, dtype=torch.float32, device=device)
         self.launches = 0
 
     def _gn(self, x, wb, silu):
