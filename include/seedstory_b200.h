@@ -100,7 +100,8 @@ SS_EXPORT int ss_kv_gather_tokens_16b(void* kpool, void* vpool, int layers, long
  * epilogue order: +bias[N] -> round -> +bias2[row / rows_per_group, N] -> round -> act (1 gelu-erf,
  * 2 silu) -> round -> +residual -> round.  glu: 1 = first*gelu(second) (diffusers GEGLU), 2 =
  * silu(first)*second (LlamaMLP, :191) over interleaved column pairs, output width N/2.
- * force_bn: 0 = auto, else 64/128/160/256 (N tile).
+ * force_bn: 0 = auto, else 64/128/160/256 (N tile of the single-CTA kernel; 256 may take the CTA-pair kernel);
+ * 1160 / 1256 force the CTA-pair kernel with a 160- / 256-wide pair tile (test hooks).
  * flags: SS_GEMM_B_CONST = B is a weight matrix that no work queued on `stream` writes (an nn.Linear weight): its
  * first tiles are then fetched while the preceding kernel is still draining.  Leave it clear when B is an
  * activation (e.g. the q k^T product of the VAE mid-block attention). */

@@ -249,6 +249,153 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
 // MMA of tile i+1 overlaps the epilogue of tile i; the epilogue stages fp16/bf16 rows in swizzled shared
 // memory and writes them with TMA tile stores (full 128-byte lines, bounds clipped by the tensor map).
 // =============================================================================================
+// One accumulator tile (this CTA's 128 rows x BN columns at `taddr`) -> epilogue -> global memory, executed by one
+// epilogue warp (lane quarter q) for the fills f_begin, f_begin + f_step, ...  Shared by the persistent and the
+// CTA-pair kernel.  A fill is 64 output columns staged in 128B-swizzled shared memory and written by a TMA tile
+// store; a 160-wide tile ends in a 32-column tail that is stored straight from registers.
+template <typename T, int BN, bool REMOTE>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tmC, uint8_t* stg, uint32_t taddr,
+                                              uint64_t* full_bar, uint32_t full_parity, uint64_t* empty_bar, int n0,
+                                              int m0, int q, int lane, int f_begin, int f_step) {
+  const int r = q * 32 + lane;
+  const int acc_per_fill = p.glu ? 128 : 64;
+  constexpr int kTail = BN % 64;  // 32 for BN = 160, else 0 (a GLU tail is BN % 128 = 32 as well)
+  const int nfills = (BN + acc_per_fill - 1) / acc_per_fill;
+  const long long m = (long long)m0 + r;
+  const bool row_ok = m < (long long)p.M;
+  const T* res_row = (p.residual && row_ok) ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
+  const T* b2_row = (p.bias2 && row_ok)
+                        ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2
+                        : nullptr;
+  const T* bias = reinterpret_cast<const T*>(p.bias);
+  T* out_row = reinterpret_cast<T*>(p.out) + m * p.ldo;
+  const int n_out_cols = p.glu ? (p.N >> 1) : p.N;
+
+  // the residual of a 32-column chunk is requested one chunk ahead (the first one before the accumulator is
+  // even complete), so its global-memory latency hides behind the main loop and the previous chunk
+  vec8 nr[4];
+  auto request = [&](int col0) {
+#pragma unroll
+    for (int gI = 0; gI < 4; ++gI) {
+      const int col = col0 + gI * 8;
+      nr[gI] = (res_row && col < p.N) ? ld_cached16(res_row + col) : vec8{0u, 0u, 0u, 0u};
+    }
+  };
+  if (f_begin < nfills) request(n0 + f_begin * acc_per_fill);
+  tc::mbar_wait(full_bar, full_parity);
+  tc::fence_after_sync();
+
+#pragma unroll 1
+  for (int f = f_begin; f < nfills; f += f_step) {
+    const int c0 = f * acc_per_fill;
+    const int fill_cols = min(acc_per_fill, BN - c0);
+    const bool direct = kTail != 0 && fill_cols < acc_per_fill;  // tail: registers -> global, no staging
+    const bool last_fill = f + f_step >= nfills;
+    if (!direct) {
+      if (lane == 0) tc::tma_store_wait_read<0>();  // the previous store from this buffer has been read out
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < fill_cols; cc += 32) {
+      const int c = c0 + cc;
+      const int col0 = n0 + c;
+      vec8 vb[4], vr[4], vb2[4];
+#pragma unroll
+      for (int gI = 0; gI < 4; ++gI) {
+        vr[gI] = nr[gI];
+        const int col = col0 + gI * 8;
+        const bool col_ok = col < p.N;
+        vb[gI] = (bias && col_ok) ? ld_cached16(bias + col) : vec8{0u, 0u, 0u, 0u};
+        vb2[gI] = (b2_row && col_ok) ? ld_cached16(b2_row + col) : vec8{0u, 0u, 0u, 0u};
+      }
+      {  // next chunk of this warp: same fill, or the first chunk of its next fill
+        int nf = f, ncc = cc + 32;
+        if (ncc >= fill_cols) nf = f + f_step, ncc = 0;
+        if (nf < nfills) request(n0 + nf * acc_per_fill + ncc);
+      }
+      uint32_t raw[32];
+      tc::tmem_ld_32x32(taddr + (uint32_t)c, raw);
+      tc::tmem_ld_wait();
+      if (last_fill && cc + 32 >= fill_cols) {  // last TMEM read of this tile: hand the accumulator back
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (REMOTE)
+            tc::mbar_arrive_remote(empty_bar, 0);  // the pair's accumulator-drained barrier lives in the leader CTA
+          else
+            tc::mbar_arrive(empty_bar);
+        }
+      }
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+#pragma unroll
+      for (int gI = 0; gI < 4; ++gI) {
+        float* vv = v + gI * 8;
+        float bf[8];
+        unpack8<T>(vb[gI], bf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
+        if (p.bias2) {
+          unpack8<T>(vb2[gI], bf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
+        }
+        if (p.glu == 0) {
+          if (p.act) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(act_apply<T>(vv[i], p.act)));
+          }
+          if (p.residual) {
+            unpack8<T>(vr[gI], bf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] += bf[i];
+          }
+          if (direct) {
+            if (row_ok && col0 + gI * 8 < p.N) st16(out_row + col0 + gI * 8, pack8<T>(vv));
+          } else {
+            // 16-byte piece j of this row inside the 128-byte staging row, 128B-swizzled like the TMA expects
+            const int j = (cc >> 3) + gI;
+            *reinterpret_cast<vec8*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8<T>(vv);
+          }
+        } else {
+          T o4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = vv[2 * i], b = vv[2 * i + 1];
+            float o;
+            if (p.glu == 1)
+              o = a * ss_num<T>::to_f(ss_num<T>::from_f(gelu_erf(b)));
+            else
+              o = ss_num<T>::to_f(ss_num<T>::from_f(a / (1.f + __expf(-a)))) * b;
+            o4[i] = ss_num<T>::from_f(o);
+          }
+          // 8 accumulator columns -> 4 outputs = 8 bytes; output column within the fill = (cc + gI*8) / 2
+          const int ocol = (cc + gI * 8) >> 1;               // 0..63
+          if (direct) {
+            const int gcol = ((n0 + c0) >> 1) + ocol;
+            if (row_ok && gcol < n_out_cols)
+              *reinterpret_cast<uint2*>(out_row + gcol) = *reinterpret_cast<const uint2*>(o4);
+          } else {
+            const int j = ocol >> 3, within = (ocol & 7) * 2;  // 16-byte piece, byte offset inside it
+            *reinterpret_cast<uint2*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4) + within) =
+                *reinterpret_cast<const uint2*>(o4);
+          }
+        }
+      }
+    }
+    if (direct) continue;
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      const int out_col = p.glu ? ((n0 + c0) >> 1) : (n0 + c0);
+      if (out_col < n_out_cols && (long long)m0 + q * 32 < (long long)p.M)
+        tc::tma_store_2d(tmC, stg, out_col, m0 + q * 32);
+      tc::tma_store_commit();
+    }
+  }
+  }
+
 template <int BN>
 struct PersistLayout {
   // a stage holds KATOMS k-atoms of 64 elements: wide stages amortise the per-stage barrier round trip of the
@@ -427,14 +574,9 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
     // while the MMA warp works on the next tile.
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;   // 0 or 1
-    const int r = q * 32 + lane;
     uint8_t* stg = staging + ((grp * 4 + q) * (32 * 128));
     pdl_wait();  // residual / bias2 come from earlier kernels; our stores must not overtake their readers
-    // one staging fill = 64 output columns (128 bytes per row): 64 accumulator columns, or 128 with a GLU.  A
-    // 160-wide tile ends in a 32-column tail fill that is written straight from registers.
-    const int acc_per_fill = p.glu ? 128 : 64;
-    constexpr int kTail = BN % 64;  // 32 for BN = 160, else 0 (a GLU tail is BN % 128 = 32 as well)
-    const int nfills = (BN + acc_per_fill - 1) / acc_per_fill;
+    const int nfills = (BN + (p.glu ? 128 : 64) - 1) / (p.glu ? 128 : 64);  // see epilogue_tile()
     // one-tile CTAs (small problems): nothing to overlap with, so the two groups take alternate fills of that tile
     const bool split_cols = (total_tiles <= (int)gridDim.x) && nfills >= 2;
     const int f_begin = split_cols ? grp : 0, f_step = split_cols ? 2 : 1;
@@ -444,135 +586,8 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
       int n0, m0, img, y0, x0;
       tile_coords(tile, n0, m0, img, y0, x0);
       const uint32_t buf = lt & 1, use = lt >> 1;
-      const long long m = (long long)m0 + r;
-      const bool row_ok = m < (long long)p.M;
-      const T* res_row = (p.residual && row_ok) ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
-      const T* b2_row = (p.bias2 && row_ok)
-                            ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2
-                            : nullptr;
-      const T* bias = reinterpret_cast<const T*>(p.bias);
-      const uint32_t taddr = tmem_base + buf * L::TMEM_STRIDE + ((uint32_t)(q * 32) << 16);
-      T* out_row = reinterpret_cast<T*>(p.out) + m * p.ldo;
-      const int n_out_cols = p.glu ? (p.N >> 1) : p.N;
-
-      // the residual of a 32-column chunk is requested one chunk ahead (the first one before the accumulator is
-      // even complete), so its global-memory latency hides behind the main loop and the previous chunk
-      vec8 nr[4];
-      auto request = [&](int col0) {
-#pragma unroll
-        for (int gI = 0; gI < 4; ++gI) {
-          const int col = col0 + gI * 8;
-          nr[gI] = (res_row && col < p.N) ? ld_cached16(res_row + col) : vec8{0u, 0u, 0u, 0u};
-        }
-      };
-      if (f_begin < nfills) request(n0 + f_begin * acc_per_fill);
-      tc::mbar_wait(&tmem_full_bar[buf], use & 1);
-      tc::fence_after_sync();
-
-#pragma unroll 1
-      for (int f = f_begin; f < nfills; f += f_step) {
-        const int c0 = f * acc_per_fill;
-        const int fill_cols = min(acc_per_fill, BN - c0);
-        const bool direct = kTail != 0 && fill_cols < acc_per_fill;  // tail: registers -> global, no staging
-        const bool last_fill = f + f_step >= nfills;
-        if (!direct) {
-          if (lane == 0) tc::tma_store_wait_read<0>();  // the previous store from this buffer has been read out
-          __syncwarp();
-        }
-#pragma unroll 1
-        for (int cc = 0; cc < fill_cols; cc += 32) {
-          const int c = c0 + cc;
-          const int col0 = n0 + c;
-          vec8 vb[4], vr[4], vb2[4];
-#pragma unroll
-          for (int gI = 0; gI < 4; ++gI) {
-            vr[gI] = nr[gI];
-            const int col = col0 + gI * 8;
-            const bool col_ok = col < p.N;
-            vb[gI] = (bias && col_ok) ? ld_cached16(bias + col) : vec8{0u, 0u, 0u, 0u};
-            vb2[gI] = (b2_row && col_ok) ? ld_cached16(b2_row + col) : vec8{0u, 0u, 0u, 0u};
-          }
-          {  // next chunk of this warp: same fill, or the first chunk of its next fill
-            int nf = f, ncc = cc + 32;
-            if (ncc >= fill_cols) nf = f + f_step, ncc = 0;
-            if (nf < nfills) request(n0 + nf * acc_per_fill + ncc);
-          }
-          uint32_t raw[32];
-          tc::tmem_ld_32x32(taddr + (uint32_t)c, raw);
-          tc::tmem_ld_wait();
-          if (last_fill && cc + 32 >= fill_cols) {  // last TMEM read of this tile: hand the accumulator back
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[buf]);
-          }
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-#pragma unroll
-          for (int gI = 0; gI < 4; ++gI) {
-            float* vv = v + gI * 8;
-            float bf[8];
-            unpack8<T>(vb[gI], bf);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
-            if (p.bias2) {
-              unpack8<T>(vb2[gI], bf);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
-            }
-            if (p.glu == 0) {
-              if (p.act) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(act_apply<T>(vv[i], p.act)));
-              }
-              if (p.residual) {
-                unpack8<T>(vr[gI], bf);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] += bf[i];
-              }
-              if (direct) {
-                if (row_ok && col0 + gI * 8 < p.N) st16(out_row + col0 + gI * 8, pack8<T>(vv));
-              } else {
-                // 16-byte piece j of this row inside the 128-byte staging row, 128B-swizzled like the TMA expects
-                const int j = (cc >> 3) + gI;
-                *reinterpret_cast<vec8*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8<T>(vv);
-              }
-            } else {
-              T o4[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float a = vv[2 * i], b = vv[2 * i + 1];
-                float o;
-                if (p.glu == 1)
-                  o = a * ss_num<T>::to_f(ss_num<T>::from_f(gelu_erf(b)));
-                else
-                  o = ss_num<T>::to_f(ss_num<T>::from_f(a / (1.f + __expf(-a)))) * b;
-                o4[i] = ss_num<T>::from_f(o);
-              }
-              // 8 accumulator columns -> 4 outputs = 8 bytes; output column within the fill = (cc + gI*8) / 2
-              const int ocol = (cc + gI * 8) >> 1;               // 0..63
-              if (direct) {
-                const int gcol = ((n0 + c0) >> 1) + ocol;
-                if (row_ok && gcol < n_out_cols)
-                  *reinterpret_cast<uint2*>(out_row + gcol) = *reinterpret_cast<const uint2*>(o4);
-              } else {
-                const int j = ocol >> 3, within = (ocol & 7) * 2;  // 16-byte piece, byte offset inside it
-                *reinterpret_cast<uint2*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4) + within) =
-                    *reinterpret_cast<const uint2*>(o4);
-              }
-            }
-          }
-        }
-        if (direct) continue;
-        tc::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          const int out_col = p.glu ? ((n0 + c0) >> 1) : (n0 + c0);
-          if (out_col < n_out_cols && (long long)m0 + q * 32 < (long long)p.M)
-            tc::tma_store_2d(&tmC, stg, out_col, m0 + q * 32);
-          tc::tma_store_commit();
-        }
-      }
+      epilogue_tile<T, BN, false>(p, &tmC, stg, tmem_base + buf * L::TMEM_STRIDE + ((uint32_t)(q * 32) << 16),
+                                  &tmem_full_bar[buf], use & 1, &tmem_empty_bar[buf], n0, m0, q, lane, f_begin, f_step);
     }
     if (lane == 0) tc::tma_store_wait_all<0>();
   }
@@ -593,23 +608,25 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
 // tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs; both epilogues arrive on the
 // leader's "accumulator drained" barrier.
 // =============================================================================================
+template <int PBN>
 struct PairLayout {
-  static constexpr int BN = 256;
+  static constexpr int BN = PBN;                     // pair tile width: 256, or 160 (every SDXL width is a multiple)
   static constexpr int A_BYTES = BM * BK * 2;        // 16 KB: this CTA's 128 rows
-  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB: this CTA's half of the N tile
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 / 10 KB: this CTA's half of the N tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = (BN == 256) ? 6 : 7;
   static constexpr int STAGING_BYTES = 8 * 32 * 128;
+  static constexpr int TMEM_STRIDE = 256, TMEM_COLS = 512;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
-template <typename T, bool CONV>
+template <typename T, bool CONV, int PBN>
 __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                       const __grid_constant__ CUtensorMap tmB,
                                                                       const __grid_constant__ CUtensorMap tmC,
                                                                       const GemmParams p, int n_tiles_n,
                                                                       int total_tiles) {
-  using L = PairLayout;
+  using L = PairLayout<PBN>;
   constexpr int BN = L::BN;
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();
@@ -645,7 +662,7 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_pair_kernel(c
     tc::fence_barrier_init();
   }
   tc::cluster_sync();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
-  if (warp == 1) tc::tmem_alloc_2sm(tmem_ptr_smem, 2 * BN);
+  if (warp == 1) tc::tmem_alloc_2sm(tmem_ptr_smem, L::TMEM_COLS);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -710,7 +727,7 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_pair_kernel(c
         const uint32_t buf = lt & 1, use = lt >> 1;
         tc::mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);
         tc::fence_after_sync();
-        const uint32_t tmem_d = tmem_base + buf * BN;
+        const uint32_t tmem_d = tmem_base + buf * L::TMEM_STRIDE;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % L::STAGES;
           const uint32_t ph = (it / L::STAGES) & 1;
@@ -731,118 +748,27 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_pair_kernel(c
     // ================= epilogue (both CTAs): two groups of 4 warps, each CTA drains its own 128 rows =================
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
-    const int r = q * 32 + lane;
     uint8_t* stg = staging + ((grp * 4 + q) * (32 * 128));
     pdl_wait();
-    const int acc_per_fill_k = p.glu ? 128 : 64;
-    const bool split_cols = (total_tiles <= num_clusters) && (BN / 2 >= acc_per_fill_k);
+    const int nfills = (BN + (p.glu ? 128 : 64) - 1) / (p.glu ? 128 : 64);
+    const bool split_cols = (total_tiles <= num_clusters) && nfills >= 2;
+    const int f_begin = split_cols ? grp : 0, f_step = split_cols ? 2 : 1;
     uint32_t lt = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++lt) {
       if (!split_cols && (int)(lt & 1) != grp) continue;
-      const int c_begin = split_cols ? grp * (BN / 2) : 0;
-      const int c_end = split_cols ? (grp + 1) * (BN / 2) : BN;
       int n0, m0, img, y0, x0;
       tile_coords(tile, n0, m0, img, y0, x0);
       const uint32_t buf = lt & 1, use = lt >> 1;
-      tc::mbar_wait(&tmem_full_bar[buf], use & 1);
-      tc::fence_after_sync();
-      const long long m = (long long)m0 + r;
-      const bool row_ok = m < (long long)p.M;
-      const T* res_row = (p.residual && row_ok) ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
-      const T* b2_row = (p.bias2 && row_ok)
-                            ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2
-                            : nullptr;
-      const T* bias = reinterpret_cast<const T*>(p.bias);
-      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-      const int acc_per_fill = p.glu ? 128 : 64;
-#pragma unroll 1
-      for (int c0 = c_begin; c0 < c_end; c0 += acc_per_fill) {
-        if (lane == 0) tc::tma_store_wait_read<0>();
-        __syncwarp();
-#pragma unroll 1
-        for (int cc = 0; cc < acc_per_fill; cc += 32) {
-          const int c = c0 + cc;
-          const int col0 = n0 + c;
-          vec8 vb[4], vr[4], vb2[4];
-#pragma unroll
-          for (int gI = 0; gI < 4; ++gI) {
-            const int col = col0 + gI * 8;
-            const bool col_ok = col < p.N;
-            vb[gI] = (bias && col_ok) ? ld_cached16(bias + col) : vec8{0u, 0u, 0u, 0u};
-            vr[gI] = (res_row && col_ok) ? ld_cached16(res_row + col) : vec8{0u, 0u, 0u, 0u};
-            vb2[gI] = (b2_row && col_ok) ? ld_cached16(b2_row + col) : vec8{0u, 0u, 0u, 0u};
-          }
-          uint32_t raw[32];
-          tc::tmem_ld_32x32(taddr + (uint32_t)c, raw);
-          tc::tmem_ld_wait();
-          if (c + 32 >= c_end) {  // accumulator drained: tell the leader's MMA warp (remote arrive on its barrier)
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive_remote(&tmem_empty_bar[buf], 0);
-          }
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-#pragma unroll
-          for (int gI = 0; gI < 4; ++gI) {
-            float* vv = v + gI * 8;
-            float bf[8];
-            unpack8<T>(vb[gI], bf);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
-            if (p.bias2) {
-              unpack8<T>(vb2[gI], bf);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
-            }
-            if (p.glu == 0) {
-              if (p.act) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(act_apply<T>(vv[i], p.act)));
-              }
-              if (p.residual) {
-                unpack8<T>(vr[gI], bf);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] += bf[i];
-              }
-              const int j = (cc >> 3) + gI;
-              *reinterpret_cast<vec8*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8<T>(vv);
-            } else {
-              T o4[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float a = vv[2 * i], b = vv[2 * i + 1];
-                float o;
-                if (p.glu == 1)
-                  o = a * ss_num<T>::to_f(ss_num<T>::from_f(gelu_erf(b)));
-                else
-                  o = ss_num<T>::to_f(ss_num<T>::from_f(a / (1.f + __expf(-a)))) * b;
-                o4[i] = ss_num<T>::from_f(o);
-              }
-              const int ocol = (cc + gI * 8) >> 1;
-              const int j = ocol >> 3, within = (ocol & 7) * 2;
-              *reinterpret_cast<uint2*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4) + within) =
-                  *reinterpret_cast<const uint2*>(o4);
-            }
-          }
-        }
-        tc::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          const int out_col = p.glu ? ((n0 + c0) >> 1) : (n0 + c0);
-          const int n_out = p.glu ? (p.N >> 1) : p.N;
-          if (out_col < n_out && (long long)m0 + q * 32 < (long long)p.M)
-            tc::tma_store_2d(&tmC, stg, out_col, m0 + q * 32);
-          tc::tma_store_commit();
-        }
-      }
+      // "accumulator ready" is multicast to both CTAs' barriers; "accumulator drained" lives in the leader CTA
+      epilogue_tile<T, BN, true>(p, &tmC, stg, tmem_base + buf * L::TMEM_STRIDE + ((uint32_t)(q * 32) << 16),
+                                 &tmem_full_bar[buf], use & 1, &tmem_empty_bar[buf], n0, m0, q, lane, f_begin, f_step);
     }
     if (lane == 0) tc::tma_store_wait_all<0>();
   }
 
   tc::fence_before_sync();
-  tc::cluster_sync();  // neither CTA may free TMEM / exit while its peer can still touch the pair's resources
-  if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, 2 * BN);
+  tc::cluster_sync();  // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, L::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1020,13 +946,14 @@ int dispatch_persist(int dtype, int bn, const CUtensorMap& ta, const CUtensorMap
   }
 }
 
-template <typename T, bool CONV>
+template <typename T, bool CONV, int PBN>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const GemmParams& p, int n_tiles_n,
                 long long total_pair_tiles, cudaStream_t s) {
-  using L = PairLayout;
+  using L = PairLayout<PBN>;
   static bool attr_set = false;
   if (!attr_set) {
-    SS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<T, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    SS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<T, CONV, PBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 L::TOTAL));
     attr_set = true;
   }
   const int max_clusters = sm_count() / 2;
@@ -1045,8 +972,20 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  SS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<T, CONV>, ta, tb, tcm, p, n_tiles_n, (int)total_pair_tiles));
+  SS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<T, CONV, PBN>, ta, tb, tcm, p, n_tiles_n,
+                             (int)total_pair_tiles));
   return 0;
+}
+
+template <bool CONV>
+int dispatch_pair(int dtype, int pbn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
+                  const GemmParams& p, int n_tiles_n, long long pair_tiles, cudaStream_t s) {
+  if (dtype == SS_F16) {
+    if (pbn == 160) return launch_pair<__half, CONV, 160>(ta, tb, tcm, p, n_tiles_n, pair_tiles, s);
+    return launch_pair<__half, CONV, 256>(ta, tb, tcm, p, n_tiles_n, pair_tiles, s);
+  }
+  if (pbn == 160) return launch_pair<__nv_bfloat16, CONV, 160>(ta, tb, tcm, p, n_tiles_n, pair_tiles, s);
+  return launch_pair<__nv_bfloat16, CONV, 256>(ta, tb, tcm, p, n_tiles_n, pair_tiles, s);
 }
 
 // 0 = never, 1 = when the shape suits (default), 2 = whenever legal
@@ -1070,11 +1009,13 @@ long long tile_cost(long long m_tiles, int N, int bn) {
   return waves * (bn * eff + 24 * 100);
 }
 
-long long pair_cost(long long m_tiles, int N) {
-  const long long tiles = ((m_tiles + 1) / 2) * ((N + 255) / 256);
+long long pair_cost(long long m_tiles, int N, int pbn) {
+  const long long tiles = ((m_tiles + 1) / 2) * ((N + pbn - 1) / pbn);
   const long long clusters = sm_count() / 2;
   const long long waves = (tiles + clusters - 1) / clusters;
-  return waves * (256 * 95 + 24 * 100);
+  // per CTA the pair moves (128 + pbn/2) operand rows per K atom instead of (128 + bn): the short-K GEMMs are
+  // L2->SM bandwidth bound, so the pair's main loop is rated 5 % (256) / 15 % (160) faster than a single-CTA tile
+  return waves * (pbn * (pbn == 256 ? 95 : 85) + 24 * 100);
 }
 
 // N tile for the persistent kernel; a GLU epilogue pairs columns inside a 128-column fill, so it needs >= 128
@@ -1099,18 +1040,38 @@ int pick_bn_persist(long long m_tiles, int N, int glu, int force_bn) {
   return best;
 }
 
-// the CTA-pair kernel wants a 256-wide N tile without much padding and enough 256 x 256 tiles to fill the chip
-bool use_pair(long long m_tiles, int N, int glu, int force_bn) {
+// CTA-pair tile width for this problem: 0 (use the single-CTA persistent kernel), 160 or 256.
+// SS_GEMM_PAIR: 0 never, 1 (default) by the cost model, 2 whenever legal (256).  SS_GEMM_PAIR160=1 lets the cost model
+// pick the 160-wide pair tile as well (off by default).
+int pick_pair(long long m_tiles, int N, int glu, int force_bn) {
+  if (force_bn == 1160 || force_bn == 1256) return (N >= 160 && !(force_bn == 1160 && glu)) ? force_bn - 1000 : 0;  // test hooks
   const int mode = pair_mode();
-  if (mode == 0 || force_bn == 64 || force_bn == 128 || force_bn == 160) return false;
-  if (N < 256) return false;
-  if (mode == 2) return true;
+  if (mode == 0 || force_bn == 64 || force_bn == 128 || force_bn == 160) return 0;
+  if (N < 256) return 0;
+  if (mode == 2) return 256;
+  static int allow160 = -1;
+  if (allow160 < 0) {
+    const char* e = getenv("SS_GEMM_PAIR160");
+    allow160 = e ? atoi(e) : 0;  // measured no faster than the single-CTA 160 tile on the UNet shapes
+  }
+  const long long single = tile_cost(m_tiles, N, pick_bn_persist(m_tiles, N, glu, 0));
+  int best = 0;
+  long long best_cost = single;
   const int pad256 = (N + 255) / 256 * 256;
-  if (pad256 * 100 > N * 108) return false;
-  const long long pair_tiles = ((m_tiles + 1) / 2) * (pad256 / 256);
-  if (pair_tiles < 60) return false;
-  if (force_bn == 256) return true;
-  return pair_cost(m_tiles, N) <= tile_cost(m_tiles, N, pick_bn_persist(m_tiles, N, glu, 0));
+  const long long pair_tiles256 = ((m_tiles + 1) / 2) * (pad256 / 256);
+  if (pad256 * 100 <= N * 108 && pair_tiles256 >= 60) {
+    if (force_bn == 256) return 256;
+    const long long k = pair_cost(m_tiles, N, 256);
+    if (k <= best_cost) best = 256, best_cost = k;
+  }
+  // the 160-wide pair: no GLU (its register-stored tail is slow under the GLU epilogue), N a multiple of 160, and at
+  // least half a wave of clusters
+  if (allow160 && force_bn == 0 && !glu && N % 160 == 0 && m_tiles >= 2 &&
+      ((m_tiles + 1) / 2) * (N / 160) >= sm_count() / 4) {
+    const long long k = pair_cost(m_tiles, N, 160);
+    if (k < best_cost) best = 160, best_cost = k;
+  }
+  return best;
 }
 
 int get_out_tmap(CUtensorMap* out, const void* C, int dtype, long long M, int n_out, int ldc) {
@@ -1173,15 +1134,14 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
   if (!legacy) {
     CUtensorMap tcm;
     if (int e = get_out_tmap(&tcm, C, dtype, M, glu ? N / 2 : N, ldc)) return e;
-    if (use_pair(m_tiles, N, glu, force_bn)) {
+    if (const int pbn = pick_pair(m_tiles, N, glu, force_bn)) {
       CUtensorMap tb2;
       uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)ldb * 2};
-      uint32_t box[2] = {BK, 128};
+      uint32_t box[2] = {BK, (uint32_t)pbn / 2};
       if (int e = get_tmap(&tb2, B, dtype, 2, dims, str, box)) return e;
-      const int n_tiles_n = (N + 255) / 256;
+      const int n_tiles_n = (N + pbn - 1) / pbn;
       const long long pair_tiles = ((m_tiles + 1) / 2) * n_tiles_n;
-      if (dtype == SS_F16) return launch_pair<__half, false>(ta, tb2, tcm, p, n_tiles_n, pair_tiles, (cudaStream_t)stream);
-      return launch_pair<__nv_bfloat16, false>(ta, tb2, tcm, p, n_tiles_n, pair_tiles, (cudaStream_t)stream);
+      return dispatch_pair<false>(dtype, pbn, ta, tb2, tcm, p, n_tiles_n, pair_tiles, (cudaStream_t)stream);
     }
     const int n_tiles_n = (N + bn - 1) / bn;
     return dispatch_persist<false>(dtype, bn, ta, tb, tcm, p, n_tiles_n, m_tiles * n_tiles_n, (cudaStream_t)stream);
@@ -1241,15 +1201,14 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
   if (!legacy) {
     CUtensorMap tcm;
     if (int e = get_out_tmap(&tcm, y, dtype, (long long)Nimg * H * W, Cout, Cout)) return e;
-    if (use_pair(m_tiles, Cout, 0, force_bn)) {
+    if (const int pbn = pick_pair(m_tiles, Cout, 0, force_bn)) {
       CUtensorMap tb2;
       uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout}, str[1] = {(uint64_t)9 * Cin * 2};
-      uint32_t box[2] = {BK, 128};
+      uint32_t box[2] = {BK, (uint32_t)pbn / 2};
       if (int e = get_tmap(&tb2, w, dtype, 2, dims, str, box)) return e;
-      const int n_tiles_n2 = (Cout + 255) / 256;
+      const int n_tiles_n2 = (Cout + pbn - 1) / pbn;
       const long long pair_tiles = ((m_tiles + 1) / 2) * n_tiles_n2;
-      if (dtype == SS_F16) return launch_pair<__half, true>(ta, tb2, tcm, p, n_tiles_n2, pair_tiles, (cudaStream_t)stream);
-      return launch_pair<__nv_bfloat16, true>(ta, tb2, tcm, p, n_tiles_n2, pair_tiles, (cudaStream_t)stream);
+      return dispatch_pair<true>(dtype, pbn, ta, tb2, tcm, p, n_tiles_n2, pair_tiles, (cudaStream_t)stream);
     }
     const int n_tiles_n = (Cout + bn - 1) / bn;
     return dispatch_persist<true>(dtype, bn, ta, tb, tcm, p, n_tiles_n, m_tiles * n_tiles_n, (cudaStream_t)stream);
