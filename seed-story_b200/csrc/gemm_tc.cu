@@ -589,7 +589,8 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_persist_kerne
       epilogue_tile<T, BN, false>(p, &tmC, stg, tmem_base + buf * L::TMEM_STRIDE + ((uint32_t)(q * 32) << 16),
                                   &tmem_full_bar[buf], use & 1, &tmem_empty_bar[buf], n0, m0, q, lane, f_begin, f_step);
     }
-    if (lane == 0) tc::tma_store_wait_all<0>();
+    // the staging buffers only have to outlive the READ side of the last tile stores; the writes complete with the grid
+    if (lane == 0) tc::tma_store_wait_read<0>();
   }
 
   tc::fence_before_sync();
@@ -763,7 +764,8 @@ __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1) gemm_tc_pair_kernel(c
       epilogue_tile<T, BN, true>(p, &tmC, stg, tmem_base + buf * L::TMEM_STRIDE + ((uint32_t)(q * 32) << 16),
                                  &tmem_full_bar[buf], use & 1, &tmem_empty_bar[buf], n0, m0, q, lane, f_begin, f_step);
     }
-    if (lane == 0) tc::tma_store_wait_all<0>();
+    // the staging buffers only have to outlive the READ side of the last tile stores; the writes complete with the grid
+    if (lane == 0) tc::tma_store_wait_read<0>();
   }
 
   tc::fence_before_sync();
