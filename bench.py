@@ -241,7 +241,7 @@ def run_ours(args):
                     achieved=round(ach, 1),
                     peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(ach / peaks["tf_sustained"], 4),
                     traffic=31.8e6, traffic_note="dram__bytes_read+write of the GEGLU launch below from ncu --set full "
-                    "(profiles/r1_ncu_gemm_fmha_full.md); its algorithmic operand bytes are 31.5e6",
+                    "(profiles/r1_ncu_end_of_round_full.md); its algorithmic operand bytes are 31.5e6",
                     top_launch=dict(shape="GEGLU GEMM 2048x10240x1280 (60 launches per UNet step)", us=round(top_ms * 1e3, 1),
                                     achieved=round(top_fl / (top_ms * 1e-3) / 1e12, 1), peak=peaks["tf_burst"],
                                     frac=round(top_fl / (top_ms * 1e-3) / 1e12 / peaks["tf_burst"], 4)),
