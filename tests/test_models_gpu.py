@@ -49,11 +49,11 @@ def test_resampler_xlv2_matches_reference_golden(cuda_dev):
     assert _rel(o1, g["out1"]) < 1e-2 and _rel(o2, g["out2"]) < 1e-2, (_rel(o1, g["out1"]), _rel(o2, g["out2"]))
 
 
-def _engine_from_params(p, dev, max_new=64):
+def _engine_from_params(p, dev, max_new=64, max_batch=1):
     from seedstory import llama_engine
     cfg = llama_engine.LlamaConfig(hidden=p.hidden, inter=p.inter, heads=p.n_heads, layers=p.n_layers, vocab=p.vocab,
                                    eps=p.eps, max_pos=512)
-    eng = llama_engine.LlamaEngine(cfg, dev, max_batch=1, max_ctx=512, max_new=max_new)
+    eng = llama_engine.LlamaEngine(cfg, dev, max_batch=max_batch, max_ctx=512, max_new=max_new)
     eng.load_weights(p.embed, p.layers, p.norm, p.lm_head, lora_scaling=p.scaling)
     return eng
 
@@ -114,6 +114,47 @@ def test_llama_decode_steps_match_oracle(cuda_dev):
             feats = LO.lvlm_postprocess(gen_ref, hid[L:], 301, 8)
             e = [i for i, t in enumerate(gen) if t == 301][-1]
             assert _rel(hidden_rows[e - 8:e], feats) < 2e-2
+
+
+def test_batched_decode_equals_batch_one(cuda_dev):
+    """stories batched on one rank over the paged KV cache must produce, per sequence,
+    exactly what a batch-1 run produces (the reference ignores padding masks, modeling_llama_xformer.py:289-295)."""
+    from oracle import llama_oracle as LO
+    torch.manual_seed(1)
+    p = LO.LlamaParams.random(256, 352, 2, 3, 320, lora_r=16, seed=5, std=0.05)
+    img_ids = [300] + list(range(302, 310)) + [301]
+    prompts = [torch.randint(3, 290, (17,)), torch.randint(3, 290, (70,)), torch.randint(3, 290, (33,))]
+    steps = 12
+
+    def run(eng, group):
+        """Prefill each prompt of `group` into its slot, then `steps` graph-replayed decode steps for all of them."""
+        B = len(group)
+        firsts, lens = [], []
+        for b, ids in enumerate(group):
+            eng.reset_sequence(b)
+            emb = p.embed[ids].to(cuda_dev, torch.float16)
+            _, logits = eng.forward_chunk(b, emb, list(range(len(ids))))
+            firsts.append(eng.first_token(logits, int(ids[-1])))
+            lens.append(len(ids))
+        eng.begin_decode(firsts, lens)
+        out = [[f] for f in firsts]
+        for _ in range(steps):
+            eng.decode_step(B)
+            ids, done = eng.read_step(B)
+            for b in range(B):
+                out[b].append(ids[b])
+        return out
+
+    eng3 = _engine_from_params(p, cuda_dev, max_batch=3)
+    eng3.set_image_token_ids(img_ids, 2)
+    batched = run(eng3, prompts)
+    eng1 = _engine_from_params(p, cuda_dev, max_batch=1)
+    eng1.set_image_token_ids(img_ids, 2)
+    for b, ids in enumerate(prompts):
+        alone = run(eng1, [ids])[0]
+        # once a sequence has emitted EOS the engine keeps repeating its last id; compare up to and including EOS
+        n = alone.index(2) + 1 if 2 in alone else len(alone)
+        assert batched[b][:n] == alone[:n], (b, batched[b], alone)
 
 
 def test_sink_kv_compaction_matches_oracle_with_sliced_past(cuda_dev):
