@@ -15,7 +15,9 @@ CPU/torch restatement of the MLLM half of the SEED-Story hot path:
 
 Pinning: `oracle/pin_against_reference.py` runs the reference's own modules (imported from /root/reference,
 xformers replaced by an SDPA stand-in) against these functions and freezes tests/golden/*.pt.
-The LoRA arithmetic and the greedy loop are third-party restatements: parity for those two is UNPINNED.
+The greedy loop is additionally pinned against `transformers.GenerationMixin.generate` as installed here (5.5; the
+reference pins 4.34.0) — ids equal, hidden states within 3e-6 (tests/golden/hf_greedy_loop.pt).  The LoRA arithmetic is a
+third-party restatement (peft is absent): parity for it is UNPINNED.
 """
 import math
 

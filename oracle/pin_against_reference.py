@@ -137,6 +137,66 @@ def pin_llama():
     print("logits processor pinned")
 
 
+def pin_greedy_loop():
+    """The greedy loop + hidden-state bookkeeping lives in `transformers`, which is not vendored in the
+    reference (pinned there to 4.34.0; this container has 5.5).  Pin the oracle's restatement of it against the
+    installed `GenerationMixin.generate` driven the way models.py:146-153 drives it (input_ids + inputs_embeds, greedy,
+    the REFERENCE's AutoImageTokenGenerationProcessor, output_hidden_states) on a tiny HF LlamaForCausalLM carrying the
+    same weights.  Two prompts: free-running text, and a prompt ending in <img> so the forced image run, </img> and the
+    return to free decoding are exercised."""
+    sys.path.insert(0, REF)
+    from transformers import LlamaConfig, LlamaForCausalLM, LogitsProcessorList
+    from src.models_clm.generation import AutoImageTokenGenerationProcessor
+    hidden, inter, heads, layers, vocab = 256, 352, 2, 3, 320
+    cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads, num_key_value_heads=heads,
+                      num_hidden_layers=layers, vocab_size=vocab, rms_norm_eps=1e-5, max_position_embeddings=512,
+                      pad_token_id=0, bos_token_id=1, eos_token_id=2, attention_bias=False, mlp_bias=False,
+                      tie_word_embeddings=False)
+    cfg._attn_implementation = "eager"
+    hf = LlamaForCausalLM(cfg).eval()
+    p = LO.LlamaParams.random(hidden, inter, heads, layers, vocab, lora_r=0, seed=9, std=0.05)
+    sd = {"model.embed_tokens.weight": p.embed, "model.norm.weight": p.norm, "lm_head.weight": p.lm_head}
+    for i, L in enumerate(p.layers):
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[f"model.layers.{i}.self_attn.{n}.weight"] = L[n]
+        for n in ("gate_proj", "up_proj", "down_proj"):
+            sd[f"model.layers.{i}.mlp.{n}.weight"] = L[n]
+        sd[f"model.layers.{i}.input_layernorm.weight"] = L["input_layernorm"]
+        sd[f"model.layers.{i}.post_attention_layernorm.weight"] = L["post_attention_layernorm"]
+    missing, unexpected = hf.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+
+    class Tok:
+        def encode(self, s, add_special_tokens=False):
+            return [300] + list(range(302, 310)) + [301]
+    proc = AutoImageTokenGenerationProcessor(Tok(), num_img_gen_tokens=8)
+    img_ids = proc.img_ids_list
+    g = torch.Generator().manual_seed(3)
+    cases = []
+    for name, tail in (("text", []), ("image_run", [300])):
+        ids = torch.cat([torch.randint(3, 290, (1, 19), generator=g), torch.tensor([tail], dtype=torch.long)], 1)
+        emb = p.embed[ids]
+        with torch.no_grad():
+            out = hf.generate(input_ids=ids, inputs_embeds=emb, max_new_tokens=24, do_sample=False, num_beams=1,
+                              logits_processor=LogitsProcessorList([proc]), output_hidden_states=True,
+                              return_dict_in_generate=True, eos_token_id=2, pad_token_id=0)
+        seq_hf = out.sequences[0].tolist()
+        hs_hf = torch.cat([st[-1][0] for st in out.hidden_states], 0)
+        seq, hid, _ = LO.greedy_generate(p, ids, emb, img_ids, 2, 24)
+        assert seq == seq_hf, (name, seq, seq_hf)
+        d = _maxdiff(hs_hf, hid[:hs_hf.shape[0]])
+        assert d < 1e-4, d
+        if tail:
+            assert seq[ids.shape[1]:ids.shape[1] + 9] == list(range(302, 310)) + [301], seq
+        cases.append({"name": name, "input_ids": ids, "sequence": seq_hf, "hidden": hs_hf})
+        print(f"greedy loop pinned against transformers.generate ({name}): ids equal, max hidden diff {d:.2e}")
+    import transformers
+    torch.save({"cfg": dict(hidden=hidden, inter=inter, heads=heads, layers=layers, vocab=vocab, eps=1e-5, seed=9,
+                            std=0.05), "img_ids": img_ids, "eos": 2, "max_new_tokens": 24,
+                "transformers_version": transformers.__version__, "cases": cases},
+               os.path.join(GOLD, "hf_greedy_loop.pt"))
+
+
 def pin_vision():
     sys.path.insert(0, REF)
     from src.models import qwen_visual as QV
@@ -194,5 +254,6 @@ def pin_vision():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     pin_llama()
+    pin_greedy_loop()
     pin_vision()
     print("golden vectors written to", GOLD)

@@ -30,6 +30,24 @@ def test_oracle_llama_matches_reference_golden():
     assert (kv1[1][0] - g["k_layer1"]).abs().max() < 1e-5
 
 
+def test_oracle_greedy_loop_matches_transformers_generate_golden():
+    """tests/golden/hf_greedy_loop.pt was written by `transformers`' own GenerationMixin.generate (driven as
+    models.py:146-153 drives it, with the reference's image-token processor): ids equal, per-step hidden states equal."""
+    from oracle import llama_oracle as LO
+    g = torch.load(os.path.join(GOLD, "hf_greedy_loop.pt"))
+    c = g["cfg"]
+    p = LO.LlamaParams.random(c["hidden"], c["inter"], c["heads"], c["layers"], c["vocab"], lora_r=0, seed=c["seed"],
+                              std=c["std"])
+    for case in g["cases"]:
+        ids = case["input_ids"]
+        seq, hid, _ = LO.greedy_generate(p, ids, p.embed[ids], g["img_ids"], g["eos"], g["max_new_tokens"])
+        assert seq == case["sequence"], case["name"]
+        assert (hid[:case["hidden"].shape[0]] - case["hidden"]).abs().max() < 1e-4
+    run = [c_ for c_ in g["cases"] if c_["name"] == "image_run"][0]
+    L = run["input_ids"].shape[1]
+    assert run["sequence"][L:L + 9] == g["img_ids"][1:], "forced <img_i> run + </img> after a prompt ending in <img>"
+
+
 def test_oracle_logits_processor_matches_reference_golden():
     from oracle import llama_oracle as LO
     g = torch.load(os.path.join(GOLD, "logits_processor.pt"))

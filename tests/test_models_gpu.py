@@ -116,6 +116,31 @@ def test_llama_decode_steps_match_oracle(cuda_dev):
             assert _rel(hidden_rows[e - 8:e], feats) < 2e-2
 
 
+def test_engine_generate_matches_transformers_generate_golden(cuda_dev):
+    """The CUDA engine's greedy generation (graph-replayed decode steps, chunked image run) against the ids that
+    `transformers`' GenerationMixin.generate produced for the same weights (tests/golden/hf_greedy_loop.pt).  Free
+    tokens may differ only where fp16 rounding flips a near-tie; the forced image run must be identical."""
+    from oracle import llama_oracle as LO
+    g = torch.load(os.path.join(GOLD, "hf_greedy_loop.pt"))
+    c = g["cfg"]
+    p = LO.LlamaParams.random(c["hidden"], c["inter"], c["heads"], c["layers"], c["vocab"], lora_r=0, seed=c["seed"],
+                              std=c["std"])
+    eng = _engine_from_params(p, cuda_dev)
+    eng.set_image_token_ids(g["img_ids"], g["eos"])
+    for case in g["cases"]:
+        ids = case["input_ids"][0]
+        L = ids.numel()
+        ref = case["sequence"][L:]
+        gen, rows = eng.generate(0, ids.tolist(), p.embed[ids].to(cuda_dev, torch.float16), g["max_new_tokens"])
+        n = min(len(gen), len(ref))
+        same = sum(int(a == b) for a, b in zip(gen[:n], ref[:n]))
+        assert same >= n - 3, (case["name"], gen, ref)
+        if case["name"] == "image_run":
+            assert gen[:9] == g["img_ids"][1:], gen
+        if gen[:n] == ref[:n]:
+            assert _rel(rows, case["hidden"][L:L + rows.shape[0]]) < 2e-2
+
+
 def test_batched_decode_equals_batch_one(cuda_dev):
     """stories batched on one rank over the paged KV cache must produce, per sequence,
     exactly what a batch-1 run produces (the reference ignores padding masks, modeling_llama_xformer.py:289-295)."""
