@@ -259,7 +259,8 @@ def test_fmha_dense(cuda_dev, D):
     from seedstory import ops
     torch.manual_seed(6)
     for (B, H, Lq, Lk, causal) in [(2, 4, 64, 64, False), (1, 3, 100, 333, False), (2, 2, 257, 257, True),
-                                   (1, 2, 66, 1107, True), (1, 16, 1024, 1024, False), (2, 2, 64, 320, False)]:
+                                   (1, 2, 66, 1107, True), (1, 16, 1024, 1024, False), (2, 2, 64, 320, False),
+                                   (1, 2, 128, 100, False), (2, 3, 200, 128, False), (1, 2, 130, 130, True)]:  # one / two key tiles
         # fused qkv buffer for self-attention shapes, separate buffers otherwise
         q = torch.randn(B, Lq, H, D, device=cuda_dev).half()
         k = torch.randn(B, Lk, H, D, device=cuda_dev).half()
