@@ -12,7 +12,8 @@ independent, so N GPUs run N stories data-parallel with no data-path collective 
   value : turns/s with the start image + caption already on the device, results left on the device
   e2e   : same turns through the reference-facing API (src.* drop-ins) from HOST buffers: pinned start image and
           caption copied H2D inside the timed region, every turn's token ids and 1024x1024 uint8 image copied D2H
-  roofline     : the dominant kernel (tcgen05 GEMM / implicit-GEMM conv inside the UNet), live CUDA-event timing
+  roofline     : the dominant kernel (tcgen05 GEMM / implicit-GEMM conv inside the UNet): every launch type of one UNet
+                 step timed live as 10 back-to-back launches in a CUDA graph (CUDA events), weighted by its count
   cpu_baseline : the oracle (CPU restatement of the reference path) on a bounded sample, host cores of this box
 """
 import argparse
