@@ -381,7 +381,7 @@ class VAEDecoderEngine:
         zp[:, :lc] = z
         wq = torch.zeros((8, 8), dtype=BF16, device=self.dev)
         wq[:lc, :lc] = self.pq[0]
-        z2 = ops.gemm(zp, wq, bias=_pad_vec(self.pq[1], 8))  # [S*S, 8]
+        z2 = ops.gemm(zp, wq, bias=_pad_vec(self.pq[1], 8), w_const=False)  # [S*S, 8]; wq was just written on this stream
         x = torch.zeros((1, S, S, 64), dtype=BF16, device=self.dev)
         x[0, :, :, :lc] = z2[:, :lc].view(S, S, lc)
         h = ops.conv3x3(x, self.conv_in[0], bias=self.conv_in[1])

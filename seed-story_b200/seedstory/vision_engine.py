@@ -52,7 +52,8 @@ class ResamplerEngine:
         query = _dev16(g("query"), device)
         pos_q = _dev16(g("pos_embed"), device)
         _, q_in = ops.layernorm(query, _dev16(g("ln_q.weight"), device), _dev16(g("ln_q.bias"), device), eps, add=pos_q)
-        self.Q = ops.gemm(q_in, _dev16(wq, device), bias=_dev16(bq, device))  # [nq, E], constant
+        # w_const=False: the fp16 copy of wq is produced on this stream right before the launch
+        self.Q = ops.gemm(q_in, _dev16(wq, device), bias=_dev16(bq, device), w_const=False)  # [nq, E], constant
         self.scale = 1.0 / math.sqrt(E // heads)
 
     def __call__(self, x):
