@@ -122,12 +122,20 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(n):
+        if world == 1:
+            return n
+        t = torch.tensor([n], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
     # ---- value: device-resident inputs -----------------------------------------------------------
     stories = [synthetic_story(rank * 1000 + i) for i in range(args.warmup + args.steps)]
     dev_inputs = [(im.to(dev), cap) for im, cap in stories]
     for i in range(args.warmup):
         pipe.run_story(dev_inputs[i][0], dev_inputs[i][1], turns)
     barrier()
+    n_turns = 0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -135,31 +143,38 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.warmup, args.warmup + args.steps):
-        pipe.run_story(dev_inputs[i][0], dev_inputs[i][1], turns)
+        outs = pipe.run_story(dev_inputs[i][0], dev_inputs[i][1], turns)
+        n_turns += sum(1 for o in outs if o["has_img_output"])   # a story ends early if a turn emits no image
     e1.record()
     barrier()
     launches = _capi.launch_count() - c0
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    value = world * args.steps * turns / (ms * 1e-3)
+    n_turns_all = sum_over_ranks(n_turns)
+    value = n_turns_all / (ms * 1e-3)
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region --------------------------------------
     pinned = [(im.pin_memory(), cap) for im, cap in stories[args.warmup:]]
     host_img = torch.empty((1024, 1024, 3), dtype=torch.uint8).pin_memory()
     h2d = d2h = 0
 
+    n_turns_e2e = 0
+
     def e2e_story(im_host, cap):
-        nonlocal h2d, d2h
+        nonlocal h2d, d2h, n_turns_e2e
         im = im_host.to(dev, non_blocking=True)
         cap_dev = torch.tensor(cap, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)  # ids travel too
         h2d += im_host.numel() * 2 + cap_dev.numel() * 4
         outs = pipe.run_story(im, cap, turns, return_images=True)
         for o in outs:
+            if not o["has_img_output"]:
+                continue
+            n_turns_e2e += 1
             host_img.copy_(o["image"], non_blocking=True)
             d2h += host_img.numel() + len(o["generate_ids"]) * 8
         torch.cuda.current_stream().synchronize()
     e2e_story(*pinned[0])  # warm the path (pinned allocations)
-    h2d = d2h = 0
+    h2d = d2h = n_turns_e2e = 0
     barrier()
     e0.record()
     for im_host, cap in pinned:
@@ -167,7 +182,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = world * args.steps * turns / (ms_e2e * 1e-3)
+    e2e_value = sum_over_ranks(n_turns_e2e) / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM/conv launches of one UNet CFG step), live CUDA events ----
     peaks = load_peaks()
@@ -345,8 +360,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--turns", type=int, default=TURNS)
     ap.add_argument("--denoise-steps", type=int, default=DENOISE_STEPS)

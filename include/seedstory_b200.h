@@ -68,9 +68,12 @@ SS_EXPORT int ss_attn_decode_paged_f16(const void* q, const void* kcache, const 
                                        const int* page_table, int max_pages, void* out, float* workspace, int B, int H,
                                        int D, int splits, float scale, void* stream);
 /* AutoImageTokenGenerationProcessor.__call__ (src/models_clm/generation.py:19-31) + greedy argmax.
- * img_ids = [BOI, IMG_0..IMG_{n-3}, EOI]; NULL disables the processor. Logits are edited in place. */
+ * img_ids = [BOI, IMG_0..IMG_{n-3}, EOI]; NULL disables the processor. Logits are edited in place.
+ * suppress_ids (optional, NULL = none): transformers' SuppressTokensLogitsProcessor placed after the image
+ * processor in the `logits_processor=` list of src/models_clm/models.py:146-153 (scores[:, ids] = -inf). */
 SS_EXPORT int ss_logits_process_argmax_f16(void* logits, int ld, int V, const int* last_ids, const int* img_ids,
-                                           int n_img_ids, int* next_ids, int B, void* stream);
+                                           int n_img_ids, const int* suppress_ids, int n_suppress, int* next_ids,
+                                           int B, void* stream);
 /* embed_tokens lookup — modeling_llama_xformer.py:580-581 / models.py:127 */
 SS_EXPORT int ss_gather_rows_16b(const void* table, const int* ids, void* out, int ld_out, int ntok, int width,
                                  void* stream);

@@ -386,12 +386,14 @@ SS_API int ss_attn_decode_paged_f16(const void* q, const void* kcache, const voi
 // Semantics of AutoImageTokenGenerationProcessor (generation.py:19-31) followed by argmax:
 //   last id in img_ids[0 .. n-2]  -> scores[img_ids[idx+1]] = max(scores) + 10   (fp16 add)
 //   otherwise                     -> scores[img_ids[1 .. n-1]] = 0.0
-// then argmax with ties resolved to the lowest index.  The logits row is modified in place exactly
-// as the reference modifies `scores`.
+// then (optional) transformers' SuppressTokensLogitsProcessor: scores[suppress_ids] = -inf (applied AFTER the image
+// processor, i.e. later in the `logits_processor=` list), then argmax with ties resolved to the lowest index.
+// The logits row is modified in place exactly as the reference modifies `scores`.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) logits_argmax_kernel(__half* __restrict__ logits, int ld, int V,
                                                              const int* __restrict__ last_ids,
                                                              const int* __restrict__ img_ids, int n_img_ids,
+                                                             const int* __restrict__ suppress_ids, int n_suppress,
                                                              int* __restrict__ next_ids) {
   __shared__ float red_v[32];
   __shared__ int red_i[32];
@@ -414,6 +416,10 @@ __global__ void __launch_bounds__(1024) logits_argmax_kernel(__half* __restrict_
   const int forced = forced_s;
   if (img_ids != nullptr && forced < 0) {
     if (threadIdx.x >= 1 && threadIdx.x < n_img_ids) row[img_ids[threadIdx.x]] = __float2half_rn(0.f);
+    __syncthreads();
+  }
+  if (forced < 0 && n_suppress > 0) {  // (forced: the image processor's max is taken over the unsuppressed row)
+    if (threadIdx.x < n_suppress) row[suppress_ids[threadIdx.x]] = __float2half_rn(-INFINITY);
     __syncthreads();
   }
   float best = -INFINITY;
@@ -456,6 +462,7 @@ __global__ void __launch_bounds__(1024) logits_argmax_kernel(__half* __restrict_
       if (forced >= 0) {
         row[forced] = __hadd(__float2half_rn(best), __float2half_rn(10.f));
         next_ids[b] = forced;  // max+10 beats every other entry
+        for (int i = 0; i < n_suppress; ++i) row[suppress_ids[i]] = __float2half_rn(-INFINITY);
       } else {
         next_ids[b] = besti;
       }
@@ -464,11 +471,12 @@ __global__ void __launch_bounds__(1024) logits_argmax_kernel(__half* __restrict_
 }
 
 SS_API int ss_logits_process_argmax_f16(void* logits, int ld, int V, const int* last_ids, const int* img_ids,
-                                        int n_img_ids, int* next_ids, int B, void* stream) {
-  SS_REQUIRE(n_img_ids <= 1024, "image-token list too long");
+                                        int n_img_ids, const int* suppress_ids, int n_suppress, int* next_ids, int B,
+                                        void* stream) {
+  SS_REQUIRE(n_img_ids <= 1024 && n_suppress <= 1024, "image-token / suppress list too long");
   if (B == 0) return 0;
   logits_argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((__half*)logits, ld, V, last_ids, img_ids, n_img_ids,
-                                                             next_ids);
+                                                             suppress_ids, suppress_ids ? n_suppress : 0, next_ids);
   SS_LAUNCH_CHECK();
   return 0;
 }

@@ -86,6 +86,8 @@ class LlamaEngine:
         self.d_logits = torch.zeros((B, c.vocab), **f16)
         self.d_ws = torch.zeros(B * c.heads * self.splits * (c.head_dim + 2), dtype=torch.float32, device=device)
         self.img_ids = None
+        self.suppress_ids = None
+        self.suppress_ids_h = []
         self.eos_id = 2
         self._graphs = {}
         self._pinned_ids = torch.zeros(B, dtype=torch.int32).pin_memory()
@@ -124,6 +126,15 @@ class LlamaEngine:
         self.img_ids = torch.tensor(list(img_ids), dtype=torch.int32, device=self.dev)
         self.img_ids_h = list(img_ids)
         self.eos_id = eos_id
+        self._graphs.clear()
+
+    def set_suppress_ids(self, ids):
+        """transformers' SuppressTokensLogitsProcessor (scores[:, ids] = -inf every step), fused with the argmax."""
+        ids = sorted(set(int(i) for i in (ids or [])))
+        if ids == self.suppress_ids_h:
+            return
+        self.suppress_ids_h = ids
+        self.suppress_ids = torch.tensor(ids, dtype=torch.int32, device=self.dev) if ids else None
         self._graphs.clear()
 
     def embed_tokens(self, ids):
@@ -234,7 +245,8 @@ class LlamaEngine:
         ops.rmsnorm(h, w["norm"], c.eps, out=xn)
         ops.store_rows_indexed(xn, self.hist[:B], self.n_out[:B])
         ops.skinny_gemm(xn, w["lm_head"], out=self.d_logits[:B])
-        ops.logits_process_argmax(self.d_logits[:B], self.cur_ids[:B], self.img_ids, self.next_ids[:B])
+        ops.logits_process_argmax(self.d_logits[:B], self.cur_ids[:B], self.img_ids, self.next_ids[:B],
+                                  self.suppress_ids)
         ops.decode_advance(self.next_ids[:B], self.cur_ids[:B], self.tok_pos[:B], self.tok_slot[:B], self.seq_lens[:B],
                            self.out_ids[:B], self.n_out[:B], self.done[:B], self.eos_id, self.schedule[:B])
 
@@ -299,7 +311,7 @@ class LlamaEngine:
         """Processor + argmax on prefill logits (same kernel as the decode step)."""
         last = torch.tensor([last_id], dtype=torch.int32, device=self.dev)
         nxt = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        ops.logits_process_argmax(logits, last, self.img_ids, nxt)
+        ops.logits_process_argmax(logits, last, self.img_ids, nxt, self.suppress_ids)
         t = int(nxt.item())
         return sched0 if sched0 >= 0 else t
 
@@ -312,6 +324,9 @@ class LlamaEngine:
         assert self.max_batch >= 1 and b == 0, "single-story generate uses slot 0; batched decode goes through begin_decode/decode_step"
         c = self.cfg
         L = len(input_ids)
+        if max_new_tokens + 1 > self.max_new or L + max_new_tokens + 1 > min(self.max_pages * PAGE, c.max_pos):
+            raise _capi.SeedStoryError(f"generate({L} prompt + {max_new_tokens} new tokens) exceeds the engine's capacity "
+                                       f"(max_new {self.max_new}, max_ctx {self.max_pages * PAGE}, max_pos {c.max_pos})")
         self.reset_sequence(b)
         hn, logits = self.forward_chunk(b, inputs_embeds, list(range(L)))
         sched = [-1] * self.max_new

@@ -128,10 +128,11 @@ def attn_decode_paged(q, kcache, vcache, seq_lens, page_table, out, workspace, H
                page_table.shape[1], _p(out), _p(workspace), B, H, D, splits, ctypes.c_float(scale), _stream())
 
 
-def logits_process_argmax(logits, last_ids, img_ids, next_ids):
+def logits_process_argmax(logits, last_ids, img_ids, next_ids, suppress_ids=None):
     B, V = logits.shape
     _capi.call("ss_logits_process_argmax_f16", _p(logits), logits.stride(0), V, _p(last_ids), _p(img_ids),
-               img_ids.numel() if img_ids is not None else 0, _p(next_ids), B, _stream())
+               img_ids.numel() if img_ids is not None else 0, _p(suppress_ids),
+               suppress_ids.numel() if suppress_ids is not None else 0, _p(next_ids), B, _stream())
 
 
 def gather_rows(table, ids, out):

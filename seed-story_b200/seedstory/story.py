@@ -122,11 +122,14 @@ class StoryPipeline:
 
     def _schedule(self):
         """text tokens free (greedy), then <img> forced; the 64 queries + </img> come from the image-token processor;
-        EOS forced afterwards."""
-        from src.models_clm.generation import ForcedScheduleProcessor
+        EOS forced afterwards.  EOS and <img> are suppressed in the free slots (HF SuppressTokensLogitsProcessor
+        semantics): with random weights a greedy text token can be any id, and an early EOS would end the turn before
+        its image (the reference then ends the story, gen_george.py:208) while an early <img> would add a second
+        image run — either would make turns of different stories incomparable."""
+        from src.models_clm.generation import ForcedScheduleProcessor, SuppressTokensProcessor
         tk = self.tokenizer
         sched = [-1] * self.n_text + [tk.boi] + [-1] * 65 + [tk.eos_token_id]
-        return ForcedScheduleProcessor(sched)
+        return [ForcedScheduleProcessor(sched), SuppressTokensProcessor([tk.eos_token_id, tk.boi])]
 
     @torch.no_grad()
     def run_story(self, image_tensor, caption_ids, n_turns, decode_images=True, return_images=False, overlap=False):
@@ -140,7 +143,7 @@ class StoryPipeline:
         tk, dev = self.tokenizer, self.dev
         input_ids = [tk.bos_token_id] + list(caption_ids) + self.image_ids
         image_embeds = self.visual_encoder(image_tensor)
-        procs = [AutoImageTokenGenerationProcessor(tk, 64), self._schedule()]
+        procs = [AutoImageTokenGenerationProcessor(tk, 64)] + self._schedule()
         outs = []
         res = self.cfg["image"]
         main = torch.cuda.current_stream()
@@ -162,7 +165,11 @@ class StoryPipeline:
             out = self.agent.generate(tokenizer=tk, input_ids=ids_t, image_embeds=image_embeds,
                                       embeds_cmp_mask=embeds_cmp_mask, ids_cmp_mask=ids_cmp_mask,
                                       max_new_tokens=500, num_img_gen_tokens=64, logits_processor=procs, device=dev)
-            assert out["has_img_output"], "forced schedule must produce an image run"
+            if not out["has_img_output"]:
+                # reference behaviour (gen_george.py:208 `while output['has_img_output'] and …`): a turn without an
+                # image run ends the story; the caller counts the turns actually produced
+                outs.append(dict(generate_ids=out["generate_ids"].tolist(), image=None, has_img_output=False))
+                break
             img = None
             if decode_images:
                 feat = out["img_gen_feat"]
@@ -179,7 +186,7 @@ class StoryPipeline:
                                                  input_image_size=self.cfg["vit"]["image_size"])
                 img = imgs[0]
             gen = out["generate_ids"].tolist()
-            outs.append(dict(generate_ids=gen, image=img if return_images else None))
+            outs.append(dict(generate_ids=gen, image=img if return_images else None, has_img_output=True))
             image_embeds = torch.cat((image_embeds, out["img_gen_feat"]), dim=0)
             text_ids = [t for t in gen if t < tk.boi and t != tk.eos_token_id]
             input_ids = input_ids + text_ids + self.image_ids

@@ -32,3 +32,17 @@ class ForcedScheduleProcessor:
 
     def __init__(self, schedule):
         self.schedule = list(schedule)
+
+
+class SuppressTokensProcessor:
+    """transformers' SuppressTokensLogitsProcessor (`scores[:, suppress_tokens] = -inf` at every step), accepted in
+    the same `logits_processor=` list and applied on the device inside the argmax kernel.  The synthetic-weights
+    benchmark uses it to keep EOS and <img> out of the free text slots of the forced turn schedule (with random
+    weights any id can win a greedy step; the reference's trained model emits them where the story calls for them)."""
+
+    def __init__(self, suppress_tokens):
+        self.suppress_tokens = [int(t) for t in suppress_tokens]
+
+    def __call__(self, input_ids, scores):
+        scores[..., torch.tensor(self.suppress_tokens, dtype=torch.long)] = -float("inf")
+        return scores

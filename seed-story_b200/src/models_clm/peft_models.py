@@ -11,7 +11,7 @@ from torch import nn
 
 from seedstory import llama_engine
 
-from .generation import AutoImageTokenGenerationProcessor, ForcedScheduleProcessor
+from .generation import AutoImageTokenGenerationProcessor, ForcedScheduleProcessor, SuppressTokensProcessor
 
 
 class LoraConfig:
@@ -111,6 +111,10 @@ class PeftModelForCausalLM(nn.Module):
     def engine(self, max_new=512, max_ctx=4096):
         m = self.base_model.model
         dev = m.lm_head.weight.device
+        if self._engine is not None and (self._engine.max_new < max_new
+                                         or self._engine.max_pages * llama_engine.PAGE < max_ctx):
+            self._engine = None  # capacity of the cached engine is too small for this call: rebuild it
+            torch.cuda.empty_cache()
         if self._engine is None:
             eng = llama_engine.LlamaEngine(m.engine_config(), dev, max_batch=1, max_ctx=max_ctx, max_new=max_new)
             layers = []
@@ -142,11 +146,14 @@ class PeftModelForCausalLM(nn.Module):
             raise NotImplementedError("past_key_values reuse goes through LlamaEngine's paged cache (sink mode); the "
                                       "shipped scripts pass None (vis_george_sink.py:316)")
         assert input_ids.shape[0] == 1, "reference generate is batch-1 (models.py:157)"
-        eng = self.engine(max_new=max(512, max_new_tokens + 2))
-        img_ids, schedule = None, None
+        eng = self.engine(max_new=max(512, max_new_tokens + 2),
+                          max_ctx=max(4096, input_ids.shape[1] + max_new_tokens + 2))
+        img_ids, schedule, suppress = None, None, []
         for proc in (logits_processor or []):
             if isinstance(proc, ForcedScheduleProcessor):
                 schedule = proc.schedule
+            elif isinstance(proc, SuppressTokensProcessor) or hasattr(proc, "suppress_tokens"):
+                suppress = list(proc.suppress_tokens)
             elif hasattr(proc, "img_ids_list"):
                 img_ids = proc.img_ids_list
             else:
@@ -156,6 +163,7 @@ class PeftModelForCausalLM(nn.Module):
             eng._graphs.clear()
         elif getattr(eng, "img_ids_h", None) != list(img_ids) or eng.eos_id != eos_token_id:
             eng.set_image_token_ids(img_ids, eos_token_id)
+        eng.set_suppress_ids(suppress)
         ids = input_ids[0].tolist()
         if inputs_embeds is None:
             inputs_embeds = self.get_input_embeddings()(input_ids)

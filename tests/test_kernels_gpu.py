@@ -160,6 +160,25 @@ def test_logits_processor_argmax(cuda_dev):
     # processor disabled
     ops.logits_process_argmax(ref_logits, last, None, nxt)
     assert nxt.tolist() == torch.argmax(ref_logits.float(), -1).tolist()
+    # SuppressTokensLogitsProcessor after the image processor: scores[:, ids] = -inf, in place
+    from src.models_clm.generation import AutoImageTokenGenerationProcessor, SuppressTokensProcessor
+    logits = torch.randn(B, V, device=cuda_dev).half()
+    win = torch.argmax(logits[0].float()).item()
+    sup = torch.tensor([2, 32000, win], device=cuda_dev, dtype=torch.int32)
+    logits[3, 2] = 40.0               # EOS would win row 3
+    ref = logits.clone().cpu()
+    ops.logits_process_argmax(logits, last, img_ids, nxt, sup)
+
+    class _Tok:
+        def encode(self, text, add_special_tokens=False):
+            return ids
+    host = AutoImageTokenGenerationProcessor(_Tok(), 64)
+    sp = SuppressTokensProcessor(sup.tolist())
+    for b in range(B):
+        row = sp(None, host(last[b:b + 1].cpu().view(1, 1).long(), ref[b:b + 1].clone()))[0]
+        assert torch.equal(row, logits[b].cpu()), f"row {b}: in-place edits differ from the host processors"
+        assert nxt[b].item() == int(torch.argmax(row.float()).item())
+    assert nxt[0].item() != win and nxt[3].item() != 2
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])

@@ -99,3 +99,40 @@ def test_story_pipeline_tiny_end_to_end(cuda_dev):
     outs3 = pipe.run_story(img, cap, n_turns=3, return_images=True, overlap=True)
     assert [o["generate_ids"] for o in outs] == [o["generate_ids"] for o in outs3]
     assert all(torch.equal(a["image"], b["image"]) for a, b in zip(outs, outs3))
+
+
+def test_many_synthetic_stories_never_lose_the_image_run(cuda_dev):
+    """Regression for the round-1 bench crash: with random weights a free greedy token can be EOS (or <img>); the
+    synthetic schedule suppresses both in the free slots, so every turn of every story has the forced structure.
+    30 stories x 3 turns at reduced dims (the bench seeds, 1000+s)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "seed-story_b200", "shims"))
+    from seedstory import story
+    pipe = story.StoryPipeline(device=cuda_dev, cfg=story.TINY, num_inference_steps=1, n_text_tokens=24, window_size=2)
+    tk = pipe.tokenizer
+    for s in range(30):
+        g = torch.Generator().manual_seed(1000 + s)
+        img = torch.randn(1, 3, 56, 56, generator=g).half().to(cuda_dev)
+        cap = torch.randint(3, 254, (16,), generator=g).tolist()
+        outs = pipe.run_story(img, cap, n_turns=3, decode_images=False)
+        assert len(outs) == 3 and all(o["has_img_output"] for o in outs), f"story {s}"
+        for o in outs:
+            gi = o["generate_ids"]
+            assert tk.eos_token_id not in gi[:24] and tk.boi not in gi[:24]
+            assert gi[24] == tk.boi and gi[89] == tk.eoi and gi[90] == tk.eos_token_id and len(gi) == 91
+
+
+def test_story_ends_like_the_reference_when_a_turn_has_no_image(cuda_dev):
+    """gen_george.py:208 — `while output['has_img_output'] and …`: a turn whose generation stops before an image run
+    ends the story (no assert, no crash).  Forced here by scheduling EOS as the first generated token."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "seed-story_b200", "shims"))
+    from seedstory import story
+    from src.models_clm.generation import ForcedScheduleProcessor
+    pipe = story.StoryPipeline(device=cuda_dev, cfg=story.TINY, num_inference_steps=1, n_text_tokens=4, window_size=2)
+    pipe._schedule = lambda: [ForcedScheduleProcessor([-1, -1, pipe.tokenizer.eos_token_id])]
+    img = torch.randn(1, 3, 56, 56, device=cuda_dev).half()
+    outs = pipe.run_story(img, [5, 9, 17], n_turns=3, decode_images=False)
+    assert len(outs) == 1 and outs[0]["has_img_output"] is False and outs[0]["generate_ids"][-1] == pipe.tokenizer.eos_token_id
