@@ -132,6 +132,10 @@ SS_EXPORT int ss_fmha_f16(const void* q, const void* k, const void* v, void* out
                           long long o_sl, long long o_sh, const int* kv_lens, const int* page_table, int max_pages,
                           float scale, int causal, void* stream);
 
+/* test hook: how many ss_fmha_f16 calls were served by the tcgen05 kernels / by the mma.sync kernel since the last
+ * reset (host-side counters; a layout the tcgen05 path declines falls back to mma.sync and shows up here) */
+SS_EXPORT int ss_fmha_path_counts(long long* tc_calls, long long* mma_calls, int reset);
+
 /* ---- bandwidth-bound glue ------------------------------------------------------------------------ */
 /* conv1 patchify of the ViT (src/models/qwen_visual.py:347,382): NCHW image -> [B*G*G, Kpad] rows */
 SS_EXPORT int ss_im2col_patch_f16(const void* img, void* out, int B, int C, int S, int P, int Kpad, void* stream);

@@ -174,15 +174,33 @@ def image_token_processor(last_id, scores, img_ids):
     return scores
 
 
+def top2_margin(scores):
+    """(top-1 minus top-2 logit) / max|logit| of a processed score row: how far the greedy choice is from a tie.
+    Test helper for the "token ids exact wherever the oracle's margin exceeds fp16 noise" rule."""
+    s = scores.float()
+    s = s[torch.isfinite(s)]
+    top = torch.topk(s, 2).values
+    return float((top[0] - top[1]) / s.abs().max().clamp_min(1e-12))
+
+
+def first_divergence(got, ref):
+    n = min(len(got), len(ref))
+    for i in range(n):
+        if got[i] != ref[i]:
+            return i
+    return n
+
+
 def greedy_generate(p, input_ids, inputs_embeds, img_ids, eos_id, max_new_tokens, use_processor=True,
-                    forced_schedule=None):
+                    forced_schedule=None, margins_out=None):
     """HF 4.34 greedy_search as configured by models.py:137-153 (batch 1).
 
     step 0 feeds inputs_embeds with position_ids = arange(L) (cumsum(ones)-1, :832-837); later steps feed the
     embedding of the last token at position len-1.  Returns (sequence ids list, final_hidden rows [L+T-1, hidden]
     where row i is the post-norm hidden state of the position whose input is sequence[i], kv caches).
     `forced_schedule`: optional list of token ids that override argmax for the first steps (synthetic-weights
-    benchmark schedule; the reference exposes the same hook through `logits_processor=`)."""
+    benchmark schedule; the reference exposes the same hook through `logits_processor=`).
+    `margins_out`: optional list that receives top2_margin() of every generated step."""
     assert input_ids.shape[0] == 1
     seq = input_ids[0].tolist()
     L = len(seq)
@@ -195,8 +213,11 @@ def greedy_generate(p, input_ids, inputs_embeds, img_ids, eos_id, max_new_tokens
         if use_processor:
             scores = image_token_processor(seq[-1], scores, img_ids)
         nxt = int(torch.argmax(scores.float()).item())
-        if forced_schedule is not None and n_new < len(forced_schedule) and forced_schedule[n_new] is not None:
+        forced = forced_schedule is not None and n_new < len(forced_schedule) and forced_schedule[n_new] is not None
+        if forced:
             nxt = forced_schedule[n_new]
+        if margins_out is not None:   # a forced step cannot flip: infinite margin
+            margins_out.append(float("inf") if forced else top2_margin(scores))
         seq.append(nxt)
         n_new += 1
         if nxt == eos_id or n_new >= max_new_tokens:

@@ -58,6 +58,15 @@ __device__ __forceinline__ vec8 ld_stream16(const void* p) {  // weights: read o
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ vec8 ld_stream_rw16(const void* p) {
+  // streamed data that an earlier kernel on the stream wrote (KV-cache pages): coherent load (no .nc — under
+  // programmatic dependent launch the producer may still be running when this kernel starts), kept out of L1
+  vec8 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 __device__ __forceinline__ vec8 ld_cached16(const void* p) {
   vec8 r;
   asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));

@@ -10,6 +10,7 @@
 //
 // v1 uses mma.sync m16n8k16 (64 query rows x 64 keys per CTA iteration); the tcgen05 version with S/P
 // in TMEM is the planned replacement.
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -283,22 +284,20 @@ int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, 
                         long long v_sb, long long v_sl, long long v_sh, long long o_sb, long long o_sl, long long o_sh,
                         float scale, int causal, cudaStream_t stream);
 
-static int fmha_tc_min_lk() {  // short key sets (UNet cross-attention: 64 context tokens) fit one mma.sync tile
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SS_FMHA_TC_MIN_LK");
-    v = e ? atoi(e) : 65;
-  }
-  return v;
-}
+static constexpr int fmha_tc_min_lk() { return 65; }  // short key sets (UNet cross-attention: 64 context tokens) fit one mma.sync tile
 
-static bool fmha_legacy() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SS_FMHA_LEGACY");
-    v = (e && e[0] == '1') ? 1 : 0;
+// which kernel family served each ss_fmha_f16 call (test hook: a tcgen05 path that silently declines a layout
+// would otherwise hide behind the mma.sync kernel's correct results)
+static std::atomic<long long> g_fmha_tc_calls{0}, g_fmha_mma_calls{0};
+
+SS_API int ss_fmha_path_counts(long long* tc_calls, long long* mma_calls, int reset) {
+  if (tc_calls) *tc_calls = g_fmha_tc_calls.load();
+  if (mma_calls) *mma_calls = g_fmha_mma_calls.load();
+  if (reset) {
+    g_fmha_tc_calls = 0;
+    g_fmha_mma_calls = 0;
   }
-  return v == 1;
+  return 0;
 }
 
 SS_API int ss_fmha_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int Lq, int Lk, int D,
@@ -310,12 +309,16 @@ SS_API int ss_fmha_f16(const void* q, const void* k, const void* v, void* out, i
   SS_REQUIRE(q_sl % 8 == 0 && k_sl % 8 == 0 && v_sl % 8 == 0 && o_sl % 2 == 0, "token strides must keep 16-byte rows");
   SS_REQUIRE(q_sh % 8 == 0 && k_sh % 8 == 0 && v_sh % 8 == 0, "head strides must keep 16-byte rows");
   if (B == 0 || H == 0 || Lq == 0) return 0;
-  if (!fmha_legacy() && page_table == nullptr && kv_lens == nullptr && Lq >= 64 && Lk >= fmha_tc_min_lk() && k_sb == v_sb) {
+  if (page_table == nullptr && kv_lens == nullptr && Lq >= 64 && Lk >= fmha_tc_min_lk() && k_sb == v_sb) {
     // tcgen05 path (S/PV accumulators in TMEM); -1 = layout not expressible as row-matrix views
     const int rc = ss_internal_fmha_tc(q, k, v, out, B, H, Lq, Lk, D, q_sb, q_sl, q_sh, k_sb, k_sl, k_sh, v_sb, v_sl, v_sh,
                                        o_sb, o_sl, o_sh, scale, causal, (cudaStream_t)stream);
-    if (rc >= 0) return rc;
+    if (rc >= 0) {
+      if (rc == 0) g_fmha_tc_calls++;
+      return rc;
+    }
   }
+  g_fmha_mma_calls++;
   FmhaParams p;
   p.q = (const __half*)q;
   p.k = (const __half*)k;

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
       const int j = jb + u * PASS + sub;
       const int jj = j < cnt ? j : 0;
       const int page = pg[jj / KV_PAGE];  // t0 is page aligned
-      kv[u] = ld_stream16(kcache + (((size_t)page * H + h) * KV_PAGE + (jj % KV_PAGE)) * D + l16 * 8);
+      kv[u] = ld_stream_rw16(kcache + (((size_t)page * H + h) * KV_PAGE + (jj % KV_PAGE)) * D + l16 * 8);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
   for (int j = warp * 2 + sub; j < cnt; j += (AD_THREADS / 32) * 2) {
     const int page = pg[j / KV_PAGE];
     float vf[8];
-    unpack8<__half>(ld_stream16(vcache + (((size_t)page * H + h) * KV_PAGE + (j % KV_PAGE)) * D + l16 * 8), vf);
+    unpack8<__half>(ld_stream_rw16(vcache + (((size_t)page * H + h) * KV_PAGE + (j % KV_PAGE)) * D + l16 * 8), vf);
     const float pj = sc[j];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += pj * vf[i];

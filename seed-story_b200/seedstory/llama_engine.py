@@ -118,6 +118,8 @@ class LlamaEngine:
         self.w = dict(layers=packed, embed=embed.to(self.dev, torch.float16).contiguous(),
                       norm=norm.to(self.dev, torch.float16).contiguous(),
                       lm_head=lm_head.to(self.dev, torch.float16).contiguous())
+        ops.register_const_tree(self.w)        # packed once here, never written again
+        torch.cuda.current_stream().synchronize()
         self._graphs.clear()
 
     def set_image_token_ids(self, img_ids, eos_id=2):

@@ -4,6 +4,7 @@ torch is used here for device memory and streams only; every function launches h
 kernels from libseedstory_b200.so and raises if the library or a CUDA device is missing.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -171,12 +172,55 @@ def lora_merge(W, A, B, scaling):
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 GLU_NONE, GLU_GEGLU, GLU_SWIGLU = 0, 1, 2
 
+# Load-time weight matrices (packed once by an engine, never written afterwards).  Only these may be fetched by a
+# GEMM before its programmatic-dependent-launch wait (SS_GEMM_B_CONST); everything else is treated as an
+# activation that an earlier kernel on the stream may still be writing.  Keyed by data pointer, validated through a
+# weak reference so a freed weight whose address is reused by an activation is not mistaken for a constant.
+_CONST_W = {}
+
+
+def register_const(t):
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        _CONST_W[t.data_ptr()] = weakref.ref(t)
+    return t
+
+
+def register_const_tree(obj, skip=("kv_ctx",), _depth=0):
+    """Register every CUDA tensor reachable through dicts / lists / tuples / plain objects under `obj`, except under
+    keys or attributes named in `skip` (per-image buffers that kernels write)."""
+    if _depth > 6:
+        return
+    if isinstance(obj, torch.Tensor):
+        register_const(obj)
+    elif isinstance(obj, dict):
+        for k, v in obj.items():
+            if k not in skip:
+                register_const_tree(v, skip, _depth + 1)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            register_const_tree(v, skip, _depth + 1)
+    elif hasattr(obj, "__dict__") and not isinstance(obj, (torch.nn.Module, type)):
+        for k, v in vars(obj).items():
+            if k not in skip:
+                register_const_tree(v, skip, _depth + 1)
+
+
+def is_const_weight(w):
+    r = _CONST_W.get(w.data_ptr())
+    if r is None:
+        return False
+    t = r()
+    return t is not None and t.data_ptr() == w.data_ptr()
+
 
 def gemm(a, w, bias=None, bias2=None, rows_per_group=0, residual=None, act=ACT_NONE, glu=GLU_NONE, alpha=1.0,
-         out=None, force_bn=0, w_const=True):
-    """out[M, N or N/2] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores.  w_const: `w` is a weight matrix that
-    nothing queued on the stream writes (SS_GEMM_B_CONST); pass False when `w` is an activation."""
+         out=None, force_bn=0, w_const=None):
+    """out[M, N or N/2] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores.  w_const (SS_GEMM_B_CONST: `w` is a
+    weight matrix nothing queued on the stream writes, so its first tiles may be fetched before the PDL wait)
+    defaults to "is `w` a registered load-time weight" (register_const); unregistered operands are activations."""
     _req_cuda(a, w)
+    if w_const is None:
+        w_const = is_const_weight(w)
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
     assert a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
@@ -237,6 +281,13 @@ def fmha(q, k, v, out, B, H, Lq, Lk, D, q_strides, k_strides, v_strides, o_strid
              ctypes.c_float(scale), 1 if causal else 0, _stream()]
     _capi.call("ss_fmha_f16", *args)
     return out
+
+
+def fmha_path_counts(reset=False):
+    """(calls served by the tcgen05 FMHA kernels, calls served by the mma.sync kernel) since the last reset."""
+    a, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    _capi.call("ss_fmha_path_counts", ctypes.byref(a), ctypes.byref(b), 1 if reset else 0)
+    return a.value, b.value
 
 
 def mha_packed(q, k, v, heads, scale, causal=False, out=None):

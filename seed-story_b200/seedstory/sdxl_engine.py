@@ -155,6 +155,8 @@ class UNetEngine:
         self.cout_pad = 8
         self.conv_out = (_pack_conv3(g("conv_out.weight"), cout_pad=self.cout_pad), _pad_vec(g("conv_out.bias"), self.cout_pad))
         self.temb_total = off[0]
+        ops.register_const_tree(self)          # load-time weights (registered BEFORE any per-image buffer exists)
+        torch.cuda.current_stream().synchronize()
         self.gn_ws = torch.zeros(2 * 2 * self.groups * 1024, dtype=torch.float32, device=device)
         self.temb_cur = torch.zeros((2, self.temb_total), dtype=F16, device=device)
         self.x_in = torch.zeros((2, self.S, self.S, self.cin_pad), dtype=F16, device=device)
@@ -354,6 +356,8 @@ class VAEDecoderEngine:
             self.up.append((res, up))
         self.norm_out = (g("decoder.conv_norm_out.weight"), g("decoder.conv_norm_out.bias"))
         self.conv_out = (_pack_conv3(g("decoder.conv_out.weight"), cout_pad=8), _pad_vec(g("decoder.conv_out.bias"), 8))
+        ops.register_const_tree(self)
+        torch.cuda.current_stream().synchronize()
         self.gn_ws = torch.zeros(2 * self.groups * 2048, dtype=torch.float32, device=device)
         self.launches = 0
 

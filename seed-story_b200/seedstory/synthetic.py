@@ -3,8 +3,19 @@
 Used by the `diffusers` façade's from_pretrained fallbacks, the tests and bench.py so that the CUDA engines and
 the oracle are driven by the SAME tensors.  SDXL-base-1.0 shapes follow SURVEY.md Appendix C."""
 import math
+import os
 
 import torch
+
+
+def missing_checkpoint(path, what):
+    """A checkpoint path that does not exist is an error, as in the reference (torch.load / HF from_pretrained
+    raise).  Seeded random weights of the real shapes are only substituted when the caller opted in with
+    SEEDSTORY_SYNTHETIC=1 (tests / benchmarks on machines without the checkpoints)."""
+    if os.environ.get("SEEDSTORY_SYNTHETIC", "0") != "1":
+        raise FileNotFoundError(f"{what}: checkpoint path {path!r} does not exist (set SEEDSTORY_SYNTHETIC=1 to run "
+                                f"with seeded random weights of the real shapes instead)")
+    print(f"[seedstory_b200] SEEDSTORY_SYNTHETIC=1: {path} not found, {what} uses seeded random weights")
 
 SDXL_UNET_CONFIG = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280), layers_per_block=2,
                         transformer_layers_per_block=(0, 2, 10), num_attention_heads=(5, 10, 20),

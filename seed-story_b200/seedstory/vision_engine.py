@@ -55,6 +55,8 @@ class ResamplerEngine:
         # w_const=False: the fp16 copy of wq is produced on this stream right before the launch
         self.Q = ops.gemm(q_in, _dev16(wq, device), bias=_dev16(bq, device), w_const=False)  # [nq, E], constant
         self.scale = 1.0 / math.sqrt(E // heads)
+        ops.register_const_tree(self)          # load-time weights: GEMMs may prefetch them before their PDL wait
+        torch.cuda.current_stream().synchronize()
 
     def __call__(self, x):
         """x [N, L, kv_dim] fp16 -> [N, nq, E]."""
@@ -119,6 +121,8 @@ class ViTEngine:
         self.ln_post = (_dev16(sd["ln_post.weight"], device), _dev16(sd["ln_post.bias"], device))
         self.proj_t = _dev16(sd["proj"].detach().t(), device)  # x @ proj  ==  x @ (proj^T)^T
         self.scale = 1.0 / math.sqrt(hd)
+        ops.register_const_tree(self)          # load-time weights: GEMMs may prefetch them before their PDL wait
+        torch.cuda.current_stream().synchronize()
 
     def __call__(self, img):
         """img [N,3,S,S] fp16 (CLIP-normalised) -> [N, nq, out_dim]."""
@@ -171,6 +175,8 @@ class ResamplerXLV2Engine:
         self.ap_v = (d(ap + "v_proj.weight"), d(ap + "v_proj.bias"))
         self.ap_c = (d(ap + "c_proj.weight"), d(ap + "c_proj.bias"))
         self.dh = self.to_q_dim() // heads
+        ops.register_const_tree(self)          # load-time weights: GEMMs may prefetch them before their PDL wait
+        torch.cuda.current_stream().synchronize()
 
     def to_q_dim(self):
         return self.layers[0]["to_q"].shape[0]

@@ -28,6 +28,22 @@ def _build_tree(root, state_dict):
         mod.register_parameter(parts[-1], nn.Parameter(val, requires_grad=False))
 
 
+def _load_config(path, defaults, renames=()):
+    """config.json of a diffusers model directory -> the subset of keys the engines use (tuples for lists)."""
+    cfg = {}
+    f = os.path.join(path, "config.json")
+    if os.path.exists(f):
+        with open(f) as fh:
+            raw = json.load(fh)
+        for src, dst in renames:
+            if src in raw and dst not in raw:
+                raw[dst] = raw[src]
+        for k in defaults:
+            if k in raw and raw[k] is not None:
+                cfg[k] = tuple(raw[k]) if isinstance(raw[k], list) else raw[k]
+    return cfg
+
+
 def _load_dir(path):
     sd = {}
     for fn in sorted(os.listdir(path)):
@@ -71,9 +87,14 @@ class UNet2DConditionModel(_Container):
     def from_pretrained(cls, path=None, subfolder=None, config=None, seed=1234, **kwargs):
         d = os.path.join(path, subfolder) if (path and subfolder) else path
         if d and os.path.isdir(d):
-            m = cls(config=config, state_dict=_load_dir(d))
-            return m
-        print(f"[seedstory_b200] {d} not found: SDXL UNet initialised with seeded random weights")
+            # SDXL's config.json calls the per-level head COUNT `attention_head_dim` (diffusers' historical naming)
+            cfg = _load_config(d, synthetic.SDXL_UNET_CONFIG, renames=[("attention_head_dim", "num_attention_heads")])
+            cfg.update(config or {})
+            for k in ("transformer_layers_per_block", "num_attention_heads"):
+                if k in cfg and not isinstance(cfg[k], tuple):
+                    cfg[k] = (cfg[k],) * len(cfg.get("block_out_channels", synthetic.SDXL_UNET_CONFIG["block_out_channels"]))
+            return cls(config=cfg, state_dict=_load_dir(d))
+        synthetic.missing_checkpoint(d, "UNet2DConditionModel")
         return cls(config=config, seed=seed)
 
     def engine(self):
@@ -94,8 +115,10 @@ class AutoencoderKL(_Container):
         d = os.path.join(path, subfolder) if (path and subfolder) else path
         if d and os.path.isdir(d):
             sd = {k: v for k, v in _load_dir(d).items() if k.startswith("decoder.") or k.startswith("post_quant_conv.")}
-            return cls(config=config, state_dict=sd)
-        print(f"[seedstory_b200] {d} not found: SDXL VAE decoder initialised with seeded random weights")
+            cfg = _load_config(d, synthetic.SDXL_VAE_CONFIG)
+            cfg.update(config or {})
+            return cls(config=cfg, state_dict=sd)
+        synthetic.missing_checkpoint(d, "AutoencoderKL")
         return cls(config=config, seed=seed)
 
     def engine(self):

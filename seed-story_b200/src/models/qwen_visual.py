@@ -132,5 +132,6 @@ class VisionTransformerWithAttnPool(_EngineMixin, nn.Module):
                 print("Load ckpt of qwen visual encoder")
                 print("missing keys: ", len(missing), "unexpected keys:", len(unexpected))
             else:
-                print(f"[seedstory_b200] {pretrained_model_path} not found: keeping seeded random ViT weights")
+                from seedstory.synthetic import missing_checkpoint
+                missing_checkpoint(pretrained_model_path, "VisionTransformerWithAttnPool")
         return model

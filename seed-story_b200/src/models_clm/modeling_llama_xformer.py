@@ -142,7 +142,8 @@ class LlamaForCausalLM(nn.Module):
             if missing:
                 raise RuntimeError(f"Llama checkpoint at {path} does not cover: {missing[:8]} …")
         else:
-            print(f"[seedstory_b200] {path} not found: Llama initialised with seeded random weights")
+            from seedstory.synthetic import missing_checkpoint
+            missing_checkpoint(path, "LlamaForCausalLM")
         return model
 
     def engine_config(self):

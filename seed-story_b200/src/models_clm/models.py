@@ -97,5 +97,6 @@ class ContinuousLVLM(nn.Module):
                 missing, unexpected = model.load_state_dict(ckpt, strict=False)
                 print('agent model, missing keys: ', len(missing), 'unexpected keys:', len(unexpected))
             else:
-                print(f"[seedstory_b200] {pretrained_model_path} not found: agent keeps seeded random weights")
+                from seedstory.synthetic import missing_checkpoint
+                missing_checkpoint(pretrained_model_path, "ContinuousLVLM (agent)")
         return model

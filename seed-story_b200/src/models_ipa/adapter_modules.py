@@ -36,7 +36,8 @@ class SDXLAdapter(nn.Module):
                 missing, unexpected = model.load_state_dict(ckpt, strict=False)
                 print('missing keys: ', len(missing), 'unexpected keys:', len(unexpected))
             else:
-                print(f"[seedstory_b200] {pretrained_model_path} not found: de-tokenizer keeps seeded random weights")
+                from seedstory.synthetic import missing_checkpoint
+                missing_checkpoint(pretrained_model_path, "SDXLAdapter (de-tokenizer)")
         return model
 
     def init_pipe(self, vae, scheduler, visual_encoder, image_transform, discrete_model=None, dtype=torch.float16,

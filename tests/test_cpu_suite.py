@@ -248,7 +248,7 @@ def test_world_size_2_sharding_gloo():
     assert d[0] != d[1], "ranks must work on different stories (seed 1000+s with s offset by rank)"
 
 
-def test_hydra_shim_instantiates_reference_style_configs(tmp_path):
+def test_hydra_shim_instantiates_reference_style_configs(tmp_path, monkeypatch):
     """One YAML = one object with `_target_` paths identical to the reference's configs."""
     import hydra
     from omegaconf import OmegaConf
@@ -262,6 +262,10 @@ def test_hydra_shim_instantiates_reference_style_configs(tmp_path):
     (tmp_path / "lora.yaml").write_text(
         "_target_: peft.LoraConfig\n_convert_: object\nr: 16\nlora_alpha: 32\nmodules_to_save:\n  - norm\n"
         "target_modules:\n  - q_proj\n  - v_proj\ntask_type: CAUSAL_LM\nlora_dropout: 0.05\n")
+    # a missing checkpoint raises like the reference's torch.load would; synthetic weights are an explicit opt-in
+    with pytest.raises(FileNotFoundError):
+        hydra.utils.instantiate(OmegaConf.load(tmp_path / "agent.yaml"), llm=torch.nn.Identity())
+    monkeypatch.setenv("SEEDSTORY_SYNTHETIC", "1")
     agent = hydra.utils.instantiate(OmegaConf.load(tmp_path / "agent.yaml"), llm=torch.nn.Identity())
     assert type(agent).__name__ == "ContinuousLVLM" and agent.input_resampler.num_queries == 64
     tf = hydra.utils.instantiate(OmegaConf.load(tmp_path / "tf.yaml"))

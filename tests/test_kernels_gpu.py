@@ -192,8 +192,10 @@ def test_gemm_tn_shapes(cuda_dev, dt):
         a = torch.randn(M, K, device=cuda_dev).to(dt)
         w = (torch.randn(N, K, device=cuda_dev) / math.sqrt(K)).to(dt)
         ref = a.float() @ w.float().t()
+        torch.cuda.synchronize()
         for bn in (0, 64, 128, 160, 256, 1160, 1256):   # 1160 / 1256: CTA-pair kernel, 160- / 256-wide pair tile
-            c = ops.gemm(a, w, force_bn=bn)
+            # alternate the weight-prefetch-before-PDL-wait path (load-time weights) and the activation-operand path
+            c = ops.gemm(a, w, force_bn=bn, w_const=(bn % 128 == 0))
             _close(c, ref, rtol=tol, atol=tol * ref.abs().max().item(), what=f"gemm {M}x{N}x{K} bn={bn} {dt}")
 
 
@@ -208,7 +210,8 @@ def test_gemm_tn_epilogues(cuda_dev, bn, M):
     N, K = 640, 320
     ops_gemm = functools.partial(ops.gemm, force_bn=bn)
     a = torch.randn(M, K, device=cuda_dev).half()
-    w = (torch.randn(N, K, device=cuda_dev) / math.sqrt(K)).half()
+    w = ops.register_const((torch.randn(N, K, device=cuda_dev) / math.sqrt(K)).half())   # a load-time weight
+    assert ops.is_const_weight(w) and not ops.is_const_weight(a)
     bias = torch.randn(N, device=cuda_dev).half()
     res = torch.randn(M, N, device=cuda_dev).half()
     rpg = (M + 2) // 3
@@ -224,6 +227,8 @@ def test_gemm_tn_epilogues(cuda_dev, bn, M):
     _close(c, 0.125 * (a.float() @ w.float().t()), what="alpha")
     # GLU epilogues over interleaved column pairs
     wp = w.view(2, N // 2, K).permute(1, 0, 2).reshape(N, K).contiguous()          # rows (first_j, second_j)
+    torch.cuda.synchronize()
+    ops.register_const(wp)
     bp = bias.view(2, N // 2).t().reshape(N).contiguous()
     first, second = lin[:, : N // 2], lin[:, N // 2:]
     c = ops_gemm(a, wp, bias=bp, glu=ops.GLU_GEGLU)

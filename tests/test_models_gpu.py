@@ -93,7 +93,9 @@ def test_llama_decode_steps_match_oracle(cuda_dev):
     emb = p.embed[ids]
     # oracle run: free-running greedy with BOI forced at generated index 6 so the image run is exercised
     sched = [None] * 6 + [300]
-    seq, hid, _ = LO.greedy_generate(p, ids, emb, img_ids, eos, max_new_tokens=24, forced_schedule=sched)
+    margins = []
+    seq, hid, _ = LO.greedy_generate(p, ids, emb, img_ids, eos, max_new_tokens=24, forced_schedule=sched,
+                                     margins_out=margins)
     gen_ref = seq[L:]
     assert gen_ref[6] == 300 and gen_ref[7:15] == list(range(302, 310)) and gen_ref[15] == 301
     eng = _engine_from_params(p, cuda_dev)
@@ -103,14 +105,15 @@ def test_llama_decode_steps_match_oracle(cuda_dev):
         gen, hidden_rows = eng.generate(0, ids[0].tolist(), emb[0].to(cuda_dev, torch.float16), 24,
                                         schedule=[t if t >= 0 else -1 for t in sch] , chunk_image_run=chunk,
                                         use_graph=chunk)
-        # forced/deterministic part must agree exactly; free tokens agree where the oracle margin allows
-        n = min(len(gen), len(gen_ref))
-        same = sum(int(a == b) for a, b in zip(gen[:n], gen_ref[:n]))
-        assert gen[6:16] == gen_ref[6:16], (gen, gen_ref)
-        assert same >= n - 3, f"too many id mismatches vs oracle: {gen} vs {gen_ref}"
-        if gen[:n] == gen_ref[:n]:
-            ref_rows = hid[L:L + hidden_rows.shape[0]]
-            assert _rel(hidden_rows, ref_rows) < 2e-2, _rel(hidden_rows, ref_rows)
+        # ids equal wherever the oracle's top-1/top-2 margin exceeds the fp16 bound; hidden rows are compared up to
+        # the first (near-tie) divergence unconditionally
+        from _parity import check_greedy_ids
+        k = check_greedy_ids(gen, gen_ref, margins, what=f"decode chunk={chunk}")
+        assert k >= 6, f"free text diverged at id {k} already: {gen} vs {gen_ref}"
+        rows = min(k, hidden_rows.shape[0])
+        assert _rel(hidden_rows[:rows], hid[L:L + rows]) < 2e-2, _rel(hidden_rows[:rows], hid[L:L + rows])
+        if k >= 16:   # the whole image run was reached on identical inputs
+            assert gen[6:16] == gen_ref[6:16], (gen, gen_ref)
             feats = LO.lvlm_postprocess(gen_ref, hid[L:], 301, 8)
             e = [i for i, t in enumerate(gen) if t == 301][-1]
             assert _rel(hidden_rows[e - 8:e], feats) < 2e-2
@@ -132,13 +135,17 @@ def test_engine_generate_matches_transformers_generate_golden(cuda_dev):
         L = ids.numel()
         ref = case["sequence"][L:]
         gen, rows = eng.generate(0, ids.tolist(), p.embed[ids].to(cuda_dev, torch.float16), g["max_new_tokens"])
-        n = min(len(gen), len(ref))
-        same = sum(int(a == b) for a, b in zip(gen[:n], ref[:n]))
-        assert same >= n - 3, (case["name"], gen, ref)
+        # margins of the (HF-pinned) oracle on the same weights: ids may differ only at a near-tie
+        from _parity import check_greedy_ids
+        margins = []
+        seq_o, _, _ = LO.greedy_generate(p, case["input_ids"], p.embed[case["input_ids"]], g["img_ids"], g["eos"],
+                                         g["max_new_tokens"], margins_out=margins)
+        assert seq_o[L:] == list(ref)
+        k = check_greedy_ids(gen, list(ref), margins, what=case["name"])
         if case["name"] == "image_run":
             assert gen[:9] == g["img_ids"][1:], gen
-        if gen[:n] == ref[:n]:
-            assert _rel(rows, case["hidden"][L:L + rows.shape[0]]) < 2e-2
+        nrow = min(k, rows.shape[0])
+        assert nrow > 0 and _rel(rows[:nrow], case["hidden"][L:L + nrow]) < 2e-2
 
 
 def test_batched_decode_equals_batch_one(cuda_dev):
