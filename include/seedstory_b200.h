@@ -97,6 +97,13 @@ SS_EXPORT int ss_kv_gather_tokens_16b(void* kpool, void* vpool, int layers, long
                                       const int* src_pages, const int* dst_pages, const int* src_idx, int n, int H,
                                       int D, void* stream);
 
+/* past_key_values ingestion (live sink-KV mode): one layer's K/V as [H, n, D] tensors with explicit head / token
+ * pitches (elements) — the reference's tuple-of-(K, V) cache layout, modeling_llama_xformer.py:241-244, as sliced and
+ * concatenated by src/inference/vis_george_sink.py:266-291 — written to token slots 0..n-1 of dst_pages. */
+SS_EXPORT int ss_kv_scatter_tokens_16b(void* kpool_layer, void* vpool_layer, const void* k_src, const void* v_src,
+                                       long long k_sh, long long k_st, long long v_sh, long long v_st,
+                                       const int* dst_pages, int n, int H, int D, void* stream);
+
 /* ---- dense contractions on tcgen05 ------------------------------------------------------------ */
 /* C[M,N] = epi(alpha * A[M,K] B[N,K]^T): every nn.Linear on the prefill / ViT / resampler / UNet /
  * VAE paths (e.g. qwen_visual.py:191,233,258-260; resampler.py:58-76; modeling_llama_xformer.py:228-230).

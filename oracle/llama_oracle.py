@@ -192,7 +192,7 @@ def first_divergence(got, ref):
 
 
 def greedy_generate(p, input_ids, inputs_embeds, img_ids, eos_id, max_new_tokens, use_processor=True,
-                    forced_schedule=None, margins_out=None):
+                    forced_schedule=None, margins_out=None, past_kvs=None, head=0):
     """HF 4.34 greedy_search as configured by models.py:137-153 (batch 1).
 
     step 0 feeds inputs_embeds with position_ids = arange(L) (cumsum(ones)-1, :832-837); later steps feed the
@@ -200,12 +200,17 @@ def greedy_generate(p, input_ids, inputs_embeds, img_ids, eos_id, max_new_tokens
     where row i is the post-norm hidden state of the position whose input is sequence[i], kv caches).
     `forced_schedule`: optional list of token ids that override argmax for the first steps (synthetic-weights
     benchmark schedule; the reference exposes the same hook through `logits_processor=`).
-    `margins_out`: optional list that receives top2_margin() of every generated step."""
+    `margins_out`: optional list that receives top2_margin() of every generated step.
+    `past_kvs`/`head`: KV reuse with `use_kv_cache_head=True` (prepare_inputs_for_generation :804-826): step 0 feeds
+    only inputs_embeds[:, head:] at positions head..L-1 on top of the given cache; the returned hidden rows then start
+    at input position `head` (models.py:186-189 keeps all of them)."""
     assert input_ids.shape[0] == 1
     seq = input_ids[0].tolist()
     L = len(seq)
-    pos = torch.arange(L).unsqueeze(0)
-    logits, hn, kvs = model_forward(p, inputs_embeds, pos, None)
+    if past_kvs is None:
+        head = 0
+    pos = torch.arange(head, L).unsqueeze(0)
+    logits, hn, kvs = model_forward(p, inputs_embeds[:, head:], pos, past_kvs)
     hiddens = [hn[0]]
     n_new = 0
     while True:
@@ -227,6 +232,17 @@ def greedy_generate(p, input_ids, inputs_embeds, img_ids, eos_id, max_new_tokens
         logits, hn, kvs = model_forward(p, emb, pos, kvs)
         hiddens.append(hn[0])
     return seq, torch.cat(hiddens, dim=0), kvs
+
+
+def lvlm_postprocess_past(sequence, rows, eoi_id, num_img_gen_tokens=64):
+    """models.py:186-197, past_key_values branch: ALL hidden rows of the call are kept and </img> is searched in the
+    last len(rows) ids of the full sequence (prompt + generated) — one position later than the rows' own inputs."""
+    tail = list(sequence)[-rows.shape[0]:]
+    eoi = [i for i, t in enumerate(tail) if t == eoi_id]
+    if not eoi:
+        return None
+    e = eoi[-1]
+    return rows[e - num_img_gen_tokens:e]
 
 
 def lvlm_postprocess(generate_ids, last_hidden_states, eoi_id, num_img_gen_tokens=64):

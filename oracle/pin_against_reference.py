@@ -8,6 +8,7 @@ the CPU test suite and the GPU parity tests have reference-generated fixtures.
 
 Reference pieces exercised (file:line):
   src/models_clm/modeling_llama_xformer.py:703-794 (LlamaForCausalLM.forward, xformers -> SDPA stand-in)
+  src/models_clm/modeling_llama_xformer.py:796-852 (prepare_inputs_for_generation, use_kv_cache_head=True KV reuse)
   src/models_clm/generation.py:9-31              (AutoImageTokenGenerationProcessor)
   src/models/qwen_visual.py:376-399, 138-150       (ViT + attn-pool, agent Resampler)
   src/models_ipa/resampler.py:228-284             (ResamplerXLV2)
@@ -251,9 +252,105 @@ def pin_vision():
                             output1_dim=96, output2_dim=160, ff_mult=4)}, os.path.join(GOLD, "resampler_xlv2.pt"))
 
 
+def pin_sink_kv_reuse():
+    """KV-reuse generation (`use_kv_cache_head=True`, the mode src/inference/vis_george_sink.py:266-295 prepares):
+    the reference's OWN prepare_inputs_for_generation (:796-852) and forward (:703-794, kv_cache_head update :780-784)
+    driven by a greedy loop written the way transformers 4.34 greedy_search drives a model
+    (prepare_inputs_for_generation -> forward -> argmax -> extend attention_mask, carry past_key_values; inputs_embeds
+    stays in model_kwargs), on a past that was sliced attention-sink style.  Freezes tests/golden/sink_kv_reuse.pt."""
+    _install_xformers_stub()
+    sys.path.insert(0, REF)
+    from src.models_clm import modeling_llama_xformer as M
+    from src.models_clm.generation import AutoImageTokenGenerationProcessor
+    from transformers import LlamaConfig
+    hidden, inter, heads, layers, vocab = 256, 352, 2, 3, 320
+    cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads,
+                      num_hidden_layers=layers, vocab_size=vocab, rms_norm_eps=1e-5, max_position_embeddings=512,
+                      pad_token_id=0)
+    cfg._attn_implementation = "eager"
+    ref = M.LlamaForCausalLM(cfg).eval()
+    p = LO.LlamaParams.random(hidden, inter, heads, layers, vocab, lora_r=0, seed=13, std=0.05)
+    sd = {"model.embed_tokens.weight": p.embed, "model.norm.weight": p.norm, "lm_head.weight": p.lm_head}
+    for i, L in enumerate(p.layers):
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[f"model.layers.{i}.self_attn.{n}.weight"] = L[n]
+        for n in ("gate_proj", "up_proj", "down_proj"):
+            sd[f"model.layers.{i}.mlp.{n}.weight"] = L[n]
+        sd[f"model.layers.{i}.input_layernorm.weight"] = L["input_layernorm"]
+        sd[f"model.layers.{i}.post_attention_layernorm.weight"] = L["post_attention_layernorm"]
+    ref.load_state_dict(sd, strict=False)
+    img_ids = [300] + list(range(302, 310)) + [301]
+    eos = 2
+
+    class _Tok:
+        def encode(self, text, add_special_tokens=False):
+            return img_ids
+    proc = AutoImageTokenGenerationProcessor(_Tok(), 8)
+    g = torch.Generator().manual_seed(17)
+    # turn 1: a 60-token context [text(10) <img> 8 queries </img> text(40)] is run in full; its cache is then sliced
+    # like the sink script does after evicting that image: first 4 slots, [boi-4, boi+8), [eoi-8, eoi+4), live tail
+    T = 60
+    ids_full = torch.randint(3, 290, (1, T), generator=g)
+    boi, eoi = 10, 19
+    ids_full[0, boi:eoi + 1] = torch.tensor(img_ids)
+    ref.use_kv_cache_head = False
+    with torch.no_grad():
+        out = ref(input_ids=ids_full, position_ids=torch.arange(T).unsqueeze(0), use_cache=True, return_dict=True)
+    keep = sorted(set(range(4)) | set(range(boi - 4, boi + 8)) | set(range(eoi - 8, eoi + 4)) | set(range(eoi + 1, T)))
+    past = tuple((k[:, :, keep], v[:, :, keep]) for (k, v) in out.past_key_values)
+    # turn 2: the windowed input_ids = live tail (40 tokens, already cached) + 7 new tokens ending in <img>
+    live = ids_full[:, eoi + 1:]
+    new = torch.cat([torch.randint(3, 290, (1, 6), generator=g), torch.tensor([[300]])], dim=1)
+    ids2 = torch.cat([live, new], dim=1)
+    head = live.shape[1]
+    L = ids2.shape[1]
+    emb2 = p.embed[ids2]
+    ref.use_kv_cache_head = True
+    ref.kv_cache_head = head
+    max_new = 14
+    seq = ids2.clone()
+    kwargs = dict(past_key_values=past, inputs_embeds=emb2, attention_mask=torch.ones(1, L, dtype=torch.long),
+                  use_cache=True)
+    hiddens, logits0 = [], None
+    with torch.no_grad():
+        for step in range(max_new):
+            mi = ref.prepare_inputs_for_generation(seq, **kwargs)
+            o = ref(**mi, return_dict=True, output_hidden_states=True)
+            if logits0 is None:
+                logits0 = o.logits.clone()
+            hiddens.append(o.hidden_states[-1][0])
+            scores = proc(seq, o.logits[:, -1, :].clone())
+            nxt = int(torch.argmax(scores[0]).item())
+            seq = torch.cat([seq, torch.tensor([[nxt]])], dim=1)
+            kwargs["past_key_values"] = o.past_key_values
+            kwargs["attention_mask"] = torch.cat([kwargs["attention_mask"], torch.ones(1, 1, dtype=torch.long)], dim=1)
+            if nxt == eos:
+                break
+    rows = torch.cat(hiddens, 0)
+    assert ref.kv_cache_head == head + (L - head) + (len(hiddens) - 1), ref.kv_cache_head
+    # oracle on the same sliced past
+    kv_o = None
+    with torch.no_grad():
+        _, _, kv_o = LO.model_forward(p, p.embed[ids_full], torch.arange(T).unsqueeze(0), None, max_pos=512)
+        past_o = [(k[:, :, keep], v[:, :, keep]) for (k, v) in kv_o]
+        seq_o, hid_o, _ = LO.greedy_generate(p, ids2, emb2, img_ids, eos, max_new, past_kvs=past_o, head=head)
+    assert seq_o == seq[0].tolist(), (seq_o, seq[0].tolist())
+    d = _maxdiff(hid_o[:rows.shape[0]], rows)
+    assert d < 2e-4, d
+    assert seq_o[L:L + 9] == img_ids[1:], "prompt ends in <img>: forced run + </img> first"
+    print("sink KV-reuse generation pinned against the reference's prepare_inputs_for_generation/forward: max hidden diff", d)
+    torch.save({"cfg": dict(hidden=hidden, inter=inter, heads=heads, layers=layers, vocab=vocab, eps=1e-5, seed=13,
+                            std=0.05),
+                "img_ids": img_ids, "eos": eos, "ids_full": ids_full, "keep": keep, "ids2": ids2, "head": head,
+                "max_new": max_new, "sequence": seq[0].tolist(), "rows": rows, "logits0": logits0,
+                "kv_cache_head_after": int(ref.kv_cache_head)},
+               os.path.join(GOLD, "sink_kv_reuse.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     pin_llama()
     pin_greedy_loop()
     pin_vision()
+    pin_sink_kv_reuse()
     print("golden vectors written to", GOLD)

@@ -614,3 +614,37 @@ SS_API int ss_kv_gather_tokens_16b(void* kpool, void* vpool, int layers, long lo
   SS_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// past_key_values ingestion: one layer's K and V given as [H, n, D] tensors (row pitch in elements per head and
+// per token, the layout of the reference's tuple-of-(K, V) cache, modeling_llama_xformer.py:241-244) are written into
+// token slots 0..n-1 of the destination page list.  Used when a caller hands `generate(past_key_values=...)` a
+// sliced / concatenated cache as src/inference/vis_george_sink.py:266-291 builds it.
+// ---------------------------------------------------------------------------------------------
+__global__ void kv_scatter_tokens_kernel(uint16_t* __restrict__ kpool, uint16_t* __restrict__ vpool,
+                                         const uint16_t* __restrict__ ksrc, const uint16_t* __restrict__ vsrc,
+                                         long long k_sh, long long k_st, long long v_sh, long long v_st,
+                                         const int* __restrict__ dst_pages, int H, int D) {
+  const int i = blockIdx.x;
+  const size_t dst = ((size_t)dst_pages[i / KV_PAGE] * H * KV_PAGE + (i % KV_PAGE)) * D;
+  const int vec_per_row = D >> 3;
+  for (int t = threadIdx.x; t < H * vec_per_row; t += blockDim.x) {
+    const int h = t / vec_per_row, v = t % vec_per_row;
+    const size_t off = (size_t)h * KV_PAGE * D + v * 8;
+    *reinterpret_cast<vec8*>(kpool + dst + off) = *reinterpret_cast<const vec8*>(ksrc + h * k_sh + i * k_st + v * 8);
+    *reinterpret_cast<vec8*>(vpool + dst + off) = *reinterpret_cast<const vec8*>(vsrc + h * v_sh + i * v_st + v * 8);
+  }
+}
+SS_API int ss_kv_scatter_tokens_16b(void* kpool_layer, void* vpool_layer, const void* k_src, const void* v_src,
+                                    long long k_sh, long long k_st, long long v_sh, long long v_st,
+                                    const int* dst_pages, int n, int H, int D, void* stream) {
+  SS_REQUIRE(D % 8 == 0 && k_sh % 8 == 0 && k_st % 8 == 0 && v_sh % 8 == 0 && v_st % 8 == 0,
+             "K/V rows must be 16-byte aligned (head_dim and pitches multiples of 8 elements)");
+  SS_REQUIRE(((reinterpret_cast<uintptr_t>(k_src) | reinterpret_cast<uintptr_t>(v_src)) & 15) == 0, "K/V base alignment");
+  if (n == 0) return 0;
+  kv_scatter_tokens_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((uint16_t*)kpool_layer, (uint16_t*)vpool_layer,
+                                                               (const uint16_t*)k_src, (const uint16_t*)v_src, k_sh, k_st,
+                                                               v_sh, v_st, dst_pages, H, D);
+  SS_LAUNCH_CHECK();
+  return 0;
+}

@@ -86,6 +86,7 @@ class LlamaEngine:
         self.d_logits = torch.zeros((B, c.vocab), **f16)
         self.d_ws = torch.zeros(B * c.heads * self.splits * (c.head_dim + 2), dtype=torch.float32, device=device)
         self.img_ids = None
+        self.img_ids_h = [-1, -2]   # no image-token processor until set_image_token_ids()
         self.suppress_ids = None
         self.suppress_ids_h = []
         self.eos_id = 2
@@ -162,6 +163,18 @@ class LlamaEngine:
             changed = True
         if changed:
             self.page_table[b].copy_(self.page_table_h[b], non_blocking=True)
+
+    def truncate(self, b, n):
+        """Drop every cache slot >= n of sequence b (e.g. the generated part of a turn, vis_george_sink.py:243: the
+        cache is cut back to the prompt).  No data moves; surplus pages return to the pool (later kernels on the
+        stream are the only possible writers, so stream order keeps this safe)."""
+        assert 0 <= n <= self.seq_len_h[b]
+        need = (n + PAGE - 1) // PAGE
+        owned = self.n_pages_owned[b]
+        if need < owned:
+            self.free_pages.extend(self.page_table_h[b, need:owned].tolist())
+            self.n_pages_owned[b] = need
+        self.seq_len_h[b] = n
 
     def retain_tokens(self, b, keep):
         """Keep only cache slots `keep` (sorted list of slot indices) of sequence b, compacted into fresh pages:
@@ -317,20 +330,60 @@ class LlamaEngine:
         t = int(nxt.item())
         return sched0 if sched0 >= 0 else t
 
+    def load_past(self, b, past):
+        """Make `past` the cache of sequence b: a sequence over layers of (K, V) tensors [1, heads, n, head_dim] — the
+        reference's `past_key_values` tuple (modeling_llama_xformer.py:241-244), e.g. the sliced / concatenated
+        attention-sink cache of src/inference/vis_george_sink.py:266-291.  K rows keep the RoPE phase they were
+        cached with.  Returns n."""
+        c = self.cfg
+        past = list(past)
+        assert len(past) == c.layers, f"past_key_values has {len(past)} layers, the model {c.layers}"
+        n = int(past[0][0].shape[2])
+        self.reset_sequence(b)
+        self._ensure_pages(b, n)
+        pages = self.page_table[b]
+        for li, (k, v) in enumerate(past):
+            assert k.shape[0] == 1 and tuple(k.shape[1:]) == (c.heads, n, c.head_dim) and v.shape == k.shape, \
+                f"layer {li}: past K/V must be [1, {c.heads}, n, {c.head_dim}]"
+            k3 = k[0].to(self.dev, torch.float16)
+            v3 = v[0].to(self.dev, torch.float16)
+            if k3.stride(2) != 1 or k3.stride(0) % 8 or k3.stride(1) % 8:
+                k3 = k3.contiguous()
+            if v3.stride(2) != 1 or v3.stride(0) % 8 or v3.stride(1) % 8:
+                v3 = v3.contiguous()
+            ops.kv_scatter_tokens(self.k_pages[li], self.v_pages[li], k3, v3, pages)
+        self.seq_len_h[b] = n
+        return n
+
     def generate(self, b, input_ids, inputs_embeds, max_new_tokens, schedule=None, chunk_image_run=True,
-                 use_graph=True):
+                 use_graph=True, past_len=None, head=0, return_chunk_hidden=False):
         """Greedy generation for sequence slot b (reference semantics: HF greedy_search with the image-token
         processor, stop on EOS or max_new_tokens).  `schedule`: optional list (len <= max_new) of forced ids
         (-1 = free).  Returns (generated ids list, hidden rows [T-1, hidden] where row i is the post-norm hidden
-        state of the position whose input is generated id i)."""
+        state of the position whose input is generated id i) [+ the post-norm hidden rows of the fed prompt chunk].
+
+        past_len=None: the sequence is reset and the whole prompt is prefilled at positions 0..L-1.
+        past_len=n (live sink-KV mode, `use_kv_cache_head=True` in the reference, prepare_inputs_for_generation
+        :804-826): the cache of slot b already holds n tokens (load_past / retain_tokens); only input_ids[head:] are
+        fed, at positions head..L-1 — positions count the CURRENT (windowed) input_ids, while the retained sink keys
+        keep the phase they were cached with — and generated token t sits at position L+t."""
         assert self.max_batch >= 1 and b == 0, "single-story generate uses slot 0; batched decode goes through begin_decode/decode_step"
         c = self.cfg
         L = len(input_ids)
-        if max_new_tokens + 1 > self.max_new or L + max_new_tokens + 1 > min(self.max_pages * PAGE, c.max_pos):
-            raise _capi.SeedStoryError(f"generate({L} prompt + {max_new_tokens} new tokens) exceeds the engine's capacity "
-                                       f"(max_new {self.max_new}, max_ctx {self.max_pages * PAGE}, max_pos {c.max_pos})")
-        self.reset_sequence(b)
-        hn, logits = self.forward_chunk(b, inputs_embeds, list(range(L)))
+        n_cached = 0 if past_len is None else int(past_len)
+        if past_len is None:
+            head = 0
+        assert 0 <= head < L, "at least one prompt token must be fed on top of the cache"
+        total = n_cached + (L - head) + max_new_tokens + 1
+        if max_new_tokens + 1 > self.max_new or total > self.max_pages * PAGE or L + max_new_tokens + 1 > c.max_pos:
+            raise _capi.SeedStoryError(f"generate({L} prompt + {max_new_tokens} new tokens on {n_cached} cached) exceeds "
+                                       f"the engine's capacity (max_new {self.max_new}, max_ctx {self.max_pages * PAGE}, "
+                                       f"max_pos {c.max_pos})")
+        if past_len is None:
+            self.reset_sequence(b)
+        else:
+            assert self.seq_len_h[b] == n_cached, (self.seq_len_h[b], n_cached)
+        hn, logits = self.forward_chunk(b, inputs_embeds[head:], list(range(head, L)))
         sched = [-1] * self.max_new
         if schedule is not None:
             sched[:len(schedule)] = schedule
@@ -359,14 +412,24 @@ class LlamaEngine:
                 self.begin_decode([gen[-1]], [L + len(gen) - 1], sched_t)
                 self.n_out[:1].fill_(len(gen))
                 armed = True
-                step0 = len(gen)
             self.decode_step(1, use_graph)
             ids, _ = self.read_step(1)
             self.seq_len_h[b] += 1
             hid_rows.append(self.hist[0, len(gen):len(gen) + 1].clone())
             gen.append(ids[0])
         hidden = torch.cat(hid_rows, 0) if hid_rows else torch.empty((0, c.hidden), dtype=torch.float16, device=self.dev)
+        if return_chunk_hidden:
+            return gen, hidden, hn
         return gen, hidden
+
+
+class RetainedKV:
+    """Engine-native `past_key_values`: "the cache of sequence b exactly as it is now" (typically right after
+    LlamaEngine.retain_tokens applied the window / attention-sink policy).  Handing this to generate() costs nothing;
+    a tuple of (K, V) tensors (the reference's data structure) is accepted as well and copied in by load_past()."""
+
+    def __init__(self, engine, b=0):
+        self.e, self.b, self.n = engine, b, engine.seq_len_h[b]
 
 
 class PagedKVView:

@@ -161,6 +161,16 @@ def kv_gather_tokens(k_pages, v_pages, src_pages, dst_pages, src_idx, H, D):
                _p(src_pages), _p(dst_pages), _p(src_idx), src_idx.numel(), H, D, _stream())
 
 
+def kv_scatter_tokens(k_pages_layer, v_pages_layer, k, v, dst_pages):
+    """k, v [H, n, D] (last dim contiguous, any head / token pitch) -> token slots 0..n-1 of dst_pages (int32, device)."""
+    _req_cuda(k, v)
+    H, n, D = k.shape
+    assert v.shape == k.shape and k.stride(2) == 1 and v.stride(2) == 1 and k.dtype == v.dtype == torch.float16
+    LL = ctypes.c_longlong
+    _capi.call("ss_kv_scatter_tokens_16b", _p(k_pages_layer), _p(v_pages_layer), _p(k), _p(v), LL(k.stride(0)),
+               LL(k.stride(1)), LL(v.stride(0)), LL(v.stride(1)), _p(dst_pages), n, H, D, _stream())
+
+
 def lora_merge(W, A, B, scaling):
     out = torch.empty_like(W)
     N, K = W.shape

@@ -132,9 +132,18 @@ class StoryPipeline:
         return [ForcedScheduleProcessor(sched), SuppressTokensProcessor([tk.eos_token_id, tk.boi])]
 
     @torch.no_grad()
-    def run_story(self, image_tensor, caption_ids, n_turns, decode_images=True, return_images=False, overlap=False):
+    def run_story(self, image_tensor, caption_ids, n_turns, decode_images=True, return_images=False, overlap=False,
+                  sink=False):
         """image_tensor [1,3,S,S] fp16 on the device (CLIP-normalised); caption_ids: list[int].
         Returns list of per-turn dicts(generate_ids, image_uint8 | None).
+
+        sink=True: LIVE multimodal attention-sink mode — what src/inference/vis_george_sink.py
+        :243-295 prepares but never switches on (it passes past_key_values=None, :316): the KV cache of the prompt is
+        kept across turns (`use_kv_cache_head=True`, kv_cache_head = previous prompt length, modeling_llama_xformer.py
+        :804-826), only the new tail [text + <img>…</img>] is fed, and when the image window overflows the cache is cut
+        to {first 4 slots} U per evicted image [<img>-4, <img>+8) U [</img>-8, </img>+4) U live tail
+        (llama_engine.sink_retained_slots); retained keys keep their RoPE phase, new tokens get window-relative
+        positions.  The image features follow the reference's KV-reuse branch (models.py:186-197).
 
         overlap=True (off by default: measured neutral on one B200, both phases already fill the GPU) issues the SDXL de-tokenizer of turn t on a side stream while the MLLM already decodes turn
         t+1: the next turn only needs `img_gen_feat` (gen_george.py:224), the pixels are merely saved
@@ -154,6 +163,9 @@ class StoryPipeline:
             side.wait_stream(main)
         else:
             side = None
+        model = self.agent.llm.base_model.model
+        model.use_kv_cache_head, model.kv_cache_head, past = bool(sink), None, None
+        n_sink = 0          # retained sink slots in front of the windowed prompt inside the cache
         for turn in range(n_turns):
             ids_t = torch.tensor([input_ids], dtype=torch.long, device=dev)
             boi = [i for i, t in enumerate(input_ids) if t == tk.boi]
@@ -164,7 +176,8 @@ class StoryPipeline:
             embeds_cmp_mask = torch.ones(image_embeds.shape[0], dtype=torch.bool, device=dev)
             out = self.agent.generate(tokenizer=tk, input_ids=ids_t, image_embeds=image_embeds,
                                       embeds_cmp_mask=embeds_cmp_mask, ids_cmp_mask=ids_cmp_mask,
-                                      max_new_tokens=500, num_img_gen_tokens=64, logits_processor=procs, device=dev)
+                                      max_new_tokens=500, num_img_gen_tokens=64, logits_processor=procs, device=dev,
+                                      past_key_values=past)
             if not out["has_img_output"]:
                 # reference behaviour (gen_george.py:208 `while output['has_img_output'] and …`): a turn without an
                 # image run ends the story; the caller counts the turns actually produced
@@ -189,11 +202,34 @@ class StoryPipeline:
             outs.append(dict(generate_ids=gen, image=img if return_images else None, has_img_output=True))
             image_embeds = torch.cat((image_embeds, out["img_gen_feat"]), dim=0)
             text_ids = [t for t in gen if t < tk.boi and t != tk.eos_token_id]
+            if not sink:
+                input_ids = input_ids + text_ids + self.image_ids
+                while image_embeds.shape[0] > self.window:  # evict the oldest image and all text before it
+                    first_eoi = input_ids.index(tk.eoi)
+                    input_ids = [tk.bos_token_id] + input_ids[first_eoi + 1:]
+                    image_embeds = image_embeds[1:]
+                continue
+            # ---- live sink mode: the cache holds [n_sink sink slots | this turn's prompt | generated ids]; keep the
+            # prompt part (vis_george_sink.py:243-244), append the next tail to the ids (:247-249)
+            from . import llama_engine
+            eng = self.agent.llm.engine()
+            L_prev = len(input_ids)
+            eng.truncate(0, n_sink + L_prev)
             input_ids = input_ids + text_ids + self.image_ids
-            while image_embeds.shape[0] > self.window:  # evict the oldest image and all text before it
-                first_eoi = input_ids.index(tk.eoi)
-                input_ids = [tk.bos_token_id] + input_ids[first_eoi + 1:]
+            while image_embeds.shape[0] > self.window:
+                b0, e0 = input_ids.index(tk.boi), input_ids.index(tk.eoi)        # oldest image, windowed indices
+                cache_len = n_sink + L_prev
+                fresh = llama_engine.sink_retained_slots(cache_len, [(n_sink + b0, n_sink + e0)], n_sink + e0 + 1,
+                                                         n_sink=4 if n_sink == 0 else 0)
+                keep = sorted(set(range(n_sink)) | set(fresh))
+                n_live = cache_len - (n_sink + e0 + 1)
+                input_ids = input_ids[e0 + 1:]
                 image_embeds = image_embeds[1:]
+                L_prev -= e0 + 1
+                eng.retain_tokens(0, keep)            # compaction: slots are contiguous again, sink slots in front
+                n_sink = len(keep) - n_live
+            model.kv_cache_head = L_prev
+            past = llama_engine.RetainedKV(eng, 0)
         if side is not None:
             main.wait_stream(side)               # every image is complete before the caller touches the results
         return outs

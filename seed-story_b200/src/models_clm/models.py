@@ -5,7 +5,8 @@ generate() keeps the reference's signature, return dict (reference :213-221) and
   embed lookup (:127) -> input_resampler on the comprehension images (:133) -> scatter into the <img_i> slots
   (:135) -> greedy generation with the image-token processor (:146-153) -> hidden rows of the 64 image queries
   before the LAST </img> (:182-197) -> output_resampler (:205) -> tokenizer.decode (:211)
-with every arithmetic step on the seedstory_b200 kernels.  The training `forward` (reference :33-96) is out of scope.
+with every arithmetic step on the seedstory_b200 kernels.  `past_key_values=` (live sink-KV mode) is honoured: a tuple
+of per-layer (K, V) tensors as vis_george_sink.py:266-291 builds it, or llama_engine.RetainedKV.  The training `forward` (reference :33-96) is out of scope.
 """
 import os
 
@@ -66,9 +67,18 @@ class ContinuousLVLM(nn.Module):
         eoi_token_id = tokenizer.encode(EOI_TOKEN, add_special_tokens=False)[0]
         attn_weights = ()
 
-        last_hidden_states = torch.cat([h[-1] for h in output.hidden_states], dim=1)
-        last_hidden_states = last_hidden_states[0, input_ids.shape[1]:, :]
-        eoi_indices = torch.where(generate_ids == eoi_token_id)[0].tolist()
+        rows = torch.cat([step[-1] for step in output.hidden_states], dim=1)[0]
+        if past_key_values is None:
+            # rows of the prompt forward are dropped; row j belongs to the position fed with generated id j (:184-185)
+            last_hidden_states = rows[input_ids.shape[1]:]
+            eoi_indices = [j for j, t in enumerate(generate_ids.tolist()) if t == eoi_token_id]
+        else:
+            # KV-reuse branch (:186-189): every row of this call is kept (the fed prompt tail + the generated
+            # positions) and </img> is searched in the LAST len(rows) ids of the sequence — i.e. shifted by one
+            # against the rows, exactly as the reference does it
+            last_hidden_states = rows
+            tail = output.sequences[0][-rows.shape[0]:].tolist()
+            eoi_indices = [j for j, t in enumerate(tail) if t == eoi_token_id]
         num_gen_imgs = 1 if len(eoi_indices) > 0 else 0
         has_img_output = num_gen_imgs > 0
         if has_img_output:

@@ -142,9 +142,6 @@ class PeftModelForCausalLM(nn.Module):
                  temperature=None, top_p=None, eos_token_id=2, **kwargs):
         if do_sample or num_beams != 1:
             raise NotImplementedError("seedstory_b200 implements the reference's greedy path (do_sample=False, num_beams=1)")
-        if past_key_values is not None:
-            raise NotImplementedError("past_key_values reuse goes through LlamaEngine's paged cache (sink mode); the "
-                                      "shipped scripts pass None (vis_george_sink.py:316)")
         assert input_ids.shape[0] == 1, "reference generate is batch-1 (models.py:157)"
         eng = self.engine(max_new=max(512, max_new_tokens + 2),
                           max_ctx=max(4096, input_ids.shape[1] + max_new_tokens + 2))
@@ -168,18 +165,35 @@ class PeftModelForCausalLM(nn.Module):
         if inputs_embeds is None:
             inputs_embeds = self.get_input_embeddings()(input_ids)
         emb = inputs_embeds[0].to(torch.float16)
-        gen, hidden = eng.generate(0, ids, emb, max_new_tokens, schedule=schedule)
-        seq = torch.tensor([ids + gen], dtype=torch.long, device=input_ids.device)
         m = self.base_model.model
+        L = len(ids)
+        past_len, head = None, 0
+        if past_key_values is not None:
+            # live KV reuse (modeling_llama_xformer.py:804-826): with use_kv_cache_head the tokens from kv_cache_head on
+            # are fed on top of the given cache at positions kv_cache_head..L-1; without it only the last token is (:827-831)
+            head = int(m.kv_cache_head) if (m.use_kv_cache_head and m.kv_cache_head is not None) else L - 1
+            if isinstance(past_key_values, llama_engine.RetainedKV):
+                assert past_key_values.e is eng and eng.seq_len_h[0] == past_key_values.n, \
+                    "RetainedKV handle is stale (the engine's cache changed since it was taken)"
+                past_len = past_key_values.n
+            else:
+                past_len = eng.load_past(0, past_key_values)
+        gen, hidden, chunk_hidden = eng.generate(0, ids, emb, max_new_tokens, schedule=schedule, past_len=past_len,
+                                                 head=head, return_chunk_hidden=True)
+        seq = torch.tensor([ids + gen], dtype=torch.long, device=input_ids.device)
         m.past_key_values = llama_engine.PagedKVView(eng, 0)
+        if m.use_kv_cache_head:
+            # LlamaForCausalLM.forward advances kv_cache_head by the tokens of every forward (:780-784)
+            fed = (L - head) + max(len(gen) - 1, 0)
+            m.kv_cache_head = fed if m.kv_cache_head is None else m.kv_cache_head + fed
         if not return_dict_in_generate:
             return seq
         hs = None
         if output_hidden_states:
-            # step 0 stands for the prompt forward (rows are never read by ContinuousLVLM.generate, models.py:184);
-            # later steps carry the post-final-norm hidden row of each generated token's input position
-            L = len(ids)
-            step0 = (torch.zeros((1, L, hidden.shape[-1]), dtype=hidden.dtype, device=hidden.device),)
+            # step 0 carries the post-final-norm hidden rows of the fed prompt chunk (read only in the past_key_values
+            # branch of ContinuousLVLM.generate, models.py:186-189); later steps the row of each generated token's
+            # input position
+            step0 = (chunk_hidden.unsqueeze(0),)
             hs = (step0,) + tuple((hidden[i:i + 1].unsqueeze(0),) for i in range(hidden.shape[0]))
         return GenerateOutput(seq, hs, None)
 

@@ -48,6 +48,37 @@ def test_oracle_greedy_loop_matches_transformers_generate_golden():
     assert run["sequence"][L:L + 9] == g["img_ids"][1:], "forced <img_i> run + </img> after a prompt ending in <img>"
 
 
+def test_oracle_sink_kv_reuse_matches_reference_golden():
+    """tests/golden/sink_kv_reuse.pt was produced by the reference's OWN prepare_inputs_for_generation / forward with
+    use_kv_cache_head=True (modeling_llama_xformer.py:796-852, :780-784) on an attention-sink-sliced past: the oracle's
+    KV-reuse mode must reproduce ids, hidden rows and the step-0 logits; and KV reuse with an UNsliced past must equal
+    a full re-prefill (causality)."""
+    from oracle import llama_oracle as LO
+    g = torch.load(os.path.join(GOLD, "sink_kv_reuse.pt"))
+    c = g["cfg"]
+    p = LO.LlamaParams.random(c["hidden"], c["inter"], c["heads"], c["layers"], c["vocab"], lora_r=0, seed=c["seed"],
+                              std=c["std"])
+    T = g["ids_full"].shape[1]
+    _, _, kv = LO.model_forward(p, p.embed[g["ids_full"]], torch.arange(T).unsqueeze(0), None, max_pos=512)
+    past = [(k[:, :, g["keep"]], v[:, :, g["keep"]]) for (k, v) in kv]
+    ids2 = g["ids2"]
+    seq, hid, _ = LO.greedy_generate(p, ids2, p.embed[ids2], g["img_ids"], g["eos"], g["max_new"], past_kvs=past,
+                                     head=g["head"])
+    assert seq == g["sequence"]
+    assert (hid[:g["rows"].shape[0]] - g["rows"]).abs().max() < 1e-4
+    L = ids2.shape[1]
+    feats = LO.lvlm_postprocess_past(seq, hid, g["img_ids"][-1], 8)
+    e = seq.index(g["img_ids"][-1], L)                 # </img> of the generated run, absolute index
+    # KV-reuse branch of models.py:186-197: the 8 rows end one position before the row fed with IMG_7
+    assert torch.equal(feats, hid[e - g["head"] - 1 - 8:e - g["head"] - 1])
+    # causality: reusing the exact prefix cache == prefilling everything
+    h = 25
+    _, _, kv_pref = LO.model_forward(p, p.embed[ids2[:, :h]], torch.arange(h).unsqueeze(0), None, max_pos=512)
+    seq_a, hid_a, _ = LO.greedy_generate(p, ids2, p.embed[ids2], g["img_ids"], g["eos"], g["max_new"], past_kvs=kv_pref, head=h)
+    seq_b, hid_b, _ = LO.greedy_generate(p, ids2, p.embed[ids2], g["img_ids"], g["eos"], g["max_new"])
+    assert seq_a == seq_b and (hid_a - hid_b[h:]).abs().max() < 1e-4
+
+
 def test_oracle_logits_processor_matches_reference_golden():
     from oracle import llama_oracle as LO
     g = torch.load(os.path.join(GOLD, "logits_processor.pt"))

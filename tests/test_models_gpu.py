@@ -216,3 +216,80 @@ def test_sink_kv_compaction_matches_oracle_with_sliced_past(cuda_dev):
     kv_s = [(k[:, :, keep], v[:, :, keep]) for (k, v) in kv]
     lo, hn_ref, _ = LO.model_forward(p, emb1, torch.tensor([pos1]), kv_s, max_pos=512)
     assert _rel(lg[0], lo[0, -1]) < 1e-2 and _rel(hn, hn_ref[0]) < 1e-2
+
+
+def test_live_sink_kv_reuse_matches_reference_golden(cuda_dev):
+    """Live KV reuse (`generate(past_key_values=…)` with use_kv_cache_head=True) on an attention-sink-sliced cache:
+    golden from the reference's own prepare_inputs_for_generation/forward (tests/golden/sink_kv_reuse.pt).  The past is
+    handed over the way vis_george_sink.py:266-291 builds it — a per-layer list of (K, V) tensors [1,H,n,D] (here:
+    non-contiguous index_select views of the full cache) — and goes through ss_kv_scatter_tokens_16b."""
+    from _parity import check_greedy_ids
+    from oracle import llama_oracle as LO
+    g = torch.load(os.path.join(GOLD, "sink_kv_reuse.pt"))
+    c = g["cfg"]
+    p = LO.LlamaParams.random(c["hidden"], c["inter"], c["heads"], c["layers"], c["vocab"], lora_r=0, seed=c["seed"],
+                              std=c["std"])
+    eng = _engine_from_params(p, cuda_dev)
+    eng.set_image_token_ids(g["img_ids"], g["eos"])
+    T = g["ids_full"].shape[1]
+    # the cache to slice comes from the engine's own full prefill (as output['past_key_values'] would)
+    eng.forward_chunk(0, p.embed[g["ids_full"][0]].to(cuda_dev, torch.float16), list(range(T)))
+    view = __import__("seedstory.llama_engine", fromlist=["PagedKVView"]).PagedKVView(eng, 0)
+    keep = torch.tensor(g["keep"], device=cuda_dev)
+    past = [[kv[:, :, keep, :] for kv in layer] for layer in view]
+    ids2 = g["ids2"][0]
+    L, head = ids2.numel(), g["head"]
+    n = eng.load_past(0, past)
+    assert n == len(g["keep"])
+    gen, rows, chunk = eng.generate(0, ids2.tolist(), p.embed[ids2].to(cuda_dev, torch.float16), g["max_new"],
+                                    past_len=n, head=head, return_chunk_hidden=True)
+    margins = []
+    _, _, kv = LO.model_forward(p, p.embed[g["ids_full"]], torch.arange(T).unsqueeze(0), None, max_pos=512)
+    past_o = [(k[:, :, g["keep"]], v[:, :, g["keep"]]) for (k, v) in kv]
+    seq_o, _, _ = LO.greedy_generate(p, g["ids2"], p.embed[g["ids2"]], g["img_ids"], g["eos"], g["max_new"],
+                                     past_kvs=past_o, head=head, margins_out=margins)
+    ref = g["sequence"][L:]
+    assert seq_o[L:] == ref
+    k = check_greedy_ids(gen, ref, margins, what="sink KV reuse")
+    assert gen[:9] == g["img_ids"][1:]                      # prompt ends in <img>: forced run first
+    assert _rel(chunk, g["rows"][:L - head]) < 1e-2, _rel(chunk, g["rows"][:L - head])
+    nrow = min(k, rows.shape[0])
+    assert _rel(rows[:nrow], g["rows"][L - head:L - head + nrow]) < 2e-2
+
+
+def test_kv_reuse_equals_full_prefill_and_truncate(cuda_dev):
+    """Property (causality): generating on top of the retained prompt cache (truncate -> RetainedKV) equals a full
+    re-prefill of the same windowed ids; and the drop-in's past_key_values branch returns the reference's KV-reuse
+    feature rows (models.py:186-197)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "seed-story_b200", "shims"))
+    from seedstory import llama_engine, story
+    pipe = story.StoryPipeline(device=cuda_dev, cfg=story.TINY, num_inference_steps=1, n_text_tokens=8, window_size=3)
+    img = torch.randn(1, 3, 56, 56, generator=torch.Generator().manual_seed(3)).half().to(cuda_dev)
+    cap = [11, 23, 35, 47, 59]
+    a = pipe.run_story(img, cap, n_turns=5, decode_images=False, sink=True)      # window 3: two evictions
+    b = pipe.run_story(img, cap, n_turns=5, decode_images=False, sink=True)
+    assert [o["generate_ids"] for o in a] == [o["generate_ids"] for o in b], "live sink mode must be deterministic"
+    tk = pipe.tokenizer
+    for o in a:
+        gi = o["generate_ids"]
+        assert o["has_img_output"] and gi[8] == tk.boi and gi[73] == tk.eoi and gi[74] == tk.eos_token_id
+    eng = pipe.agent.llm.engine()
+    # after 5 turns with window 3 the cache = sink slots + windowed prompt (+ generated part of the last turn)
+    assert eng.seq_len_h[0] < 4 * 75 + 200
+    # turn 1 is identical in both modes (no past yet); from turn 2 on the KV-reuse branch slices the feature rows one
+    # position earlier (reference models.py:186-189), so the stories legitimately diverge afterwards
+    c = pipe.run_story(img, cap, n_turns=1, decode_images=False, sink=False)
+    assert c[0]["generate_ids"] == a[0]["generate_ids"]
+    # engine-level causality check: feed [prompt | tail] in one go vs tail on the truncated prompt cache
+    e2 = pipe.agent.llm.engine()
+    ids = torch.randint(3, 250, (90,), generator=torch.Generator().manual_seed(5))
+    emb = e2.embed_tokens(ids)
+    e2.reset_sequence(0)
+    hn_full, lg_full = e2.forward_chunk(0, emb, list(range(90)))
+    e2.reset_sequence(0)
+    e2.forward_chunk(0, emb[:70], list(range(70)))
+    e2.forward_chunk(0, emb[70:80], list(range(70, 80)))     # "generated" part that the next turn drops
+    e2.truncate(0, 70)
+    hn_tail, lg_tail = e2.forward_chunk(0, emb[70:], list(range(70, 90)))
+    assert _rel(hn_tail, hn_full[70:]) < 5e-3 and _rel(lg_tail, lg_full) < 5e-3
