@@ -290,6 +290,9 @@ def fmha(q, k, v, out, B, H, Lq, Lk, D, q_strides, k_strides, v_strides, o_strid
     args += [_p(kv_lens), _p(page_table), page_table.shape[1] if page_table is not None else 0,
              ctypes.c_float(scale), 1 if causal else 0, _stream()]
     _capi.call("ss_fmha_f16", *args)
+    if RECORD is not None:
+        RECORD.append((f"fmha B{B} H{H} Lq{Lq} Lk{Lk} D{D}", 4.0 * B * H * Lq * Lk * D * (0.5 if causal and Lq == Lk else 1.0),
+                       lambda: _capi.call("ss_fmha_f16", *args)))
     return out
 
 
