@@ -153,7 +153,8 @@ SS_EXPORT int ss_add_bcast(int dtype, const void* x, const void* add, void* y, l
 SS_EXPORT int ss_scatter_rows_16b(const void* src, const int* dst_rows, void* dst, int ld_dst, int n, int width,
                                   void* stream);
 /* nn.GroupNorm(32, C) (+ optional fused SiLU) on NHWC — diffusers ResnetBlock2D / Transformer2DModel / VAE norms
- * (SURVEY.md Appendix C).  Deterministic (fixed-order) reduction; stats_ws holds ss_groupnorm_ws_floats() floats. */
+ * (SURVEY.md Appendix C).  Deterministic (fixed-order) reduction; stats_ws holds ss_groupnorm_ws_floats() floats and
+ * must be zero-filled ONCE before its first use (its first 64 words are arrival counters every call leaves at zero). */
 SS_EXPORT int ss_groupnorm_ws_floats(int N, int HW, int C, int groups);
 SS_EXPORT int ss_groupnorm_nhwc(int dtype, const void* x, void* y, const void* gamma, const void* beta,
                                 float* stats_ws, int N, int HW, int C, int groups, float eps, int silu, void* stream);

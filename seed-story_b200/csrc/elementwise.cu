@@ -95,8 +95,12 @@ SS_API int ss_scatter_rows_16b(const void* src, const int* dst_rows, void* dst, 
 // affine, optional SiLU.
 template <typename T>
 __global__ void groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW, int C,
-                                         int groups, int pix_per_cta) {
+                                         int groups, int pix_per_cta, float* __restrict__ stats,
+                                         unsigned int* __restrict__ tickets, float inv_cnt, float eps) {
   extern __shared__ float gsm[];  // [nl][2*C]
+  __shared__ int is_last;
+  pdl_trigger();
+  pdl_wait();  // x comes from the preceding kernel
   const int n = blockIdx.y;
   const int vecs = C >> 3;
   const int nl = blockDim.x / vecs;  // pixel lanes
@@ -139,31 +143,37 @@ __global__ void groupnorm_partial_kernel(const T* __restrict__ x, float* __restr
     out[0] = s;
     out[1] = q;
   }
-}
-
-// one warp per (image, group): lanes stride over the per-CTA partials, then a fixed-order butterfly (deterministic)
-__global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int chunks,
-                                          int groups, float inv_cnt, float eps, int total) {
-  pdl_trigger();
-  pdl_wait();
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (n, g)
-  const int lane = threadIdx.x & 31;
-  if (i >= total) return;
-  const int n = i / groups, g = i % groups;
-  float s = 0.f, q = 0.f;
-  for (int c = lane; c < chunks; c += 32) {
-    const float* p = partial + (((size_t)n * chunks + c) * groups + g) * 2;
-    s += p[0];
-    q += p[1];
+  // The CTA that finishes LAST for image n folds the per-CTA partials into (mean, rstd): one warp per group, lanes
+  // stride over the partials, fixed-order butterfly — the reduction order does not depend on which CTA does it, so
+  // results stay bit-reproducible.  (Replaces a separate finalize launch.)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[n], 1u);
+    is_last = (t == gridDim.x - 1);
   }
-  s = warp_sum(s);
-  q = warp_sum(q);
-  if (lane == 0) {
-    const float mean = s * inv_cnt;
-    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
-    stats[2 * i] = mean;
-    stats[2 * i + 1] = rsqrtf(var + eps);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int chunks = gridDim.x;
+  const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < groups; g += nwarps) {
+    float s = 0.f, q = 0.f;
+    for (int c = wl; c < chunks; c += 32) {
+      const float* p = partial + (((size_t)n * chunks + c) * groups + g) * 2;
+      s += __ldcg(p);
+      q += __ldcg(p + 1);
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (wl == 0) {
+      const float mean = s * inv_cnt;
+      const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+      stats[2 * ((size_t)n * groups + g)] = mean;
+      stats[2 * ((size_t)n * groups + g) + 1] = rsqrtf(var + eps);
+    }
   }
+  if (threadIdx.x == 0) tickets[n] = 0u;  // ready for the next call on this workspace
 }
 
 // apply: same (chunk, image) geometry as the partial kernel, so every thread owns one 8-channel vector — gamma,
@@ -172,6 +182,8 @@ template <typename T>
 __global__ void groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
                                        const T* __restrict__ gamma, const T* __restrict__ beta, int HW, int C,
                                        int groups, int silu, int pix_per_cta) {
+  pdl_trigger();
+  pdl_wait();  // statistics (and x) come from the preceding kernels
   const int n = blockIdx.y;
   const int vecs = C >> 3, cg = C / groups;
   const int nl = blockDim.x / vecs;
@@ -209,7 +221,10 @@ __global__ void groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ 
   }
 }
 
-// workspace layout (floats): [2*N*groups stats][N*chunks*groups*2 partials]; ss_groupnorm_ws_floats() sizes it.
+// workspace layout (32-bit words): [64 arrival tickets (uint32; must be ZERO before the first call, every call leaves
+// them at zero — a fixed location, so calls of different shapes can share one workspace)][2*N*groups stats]
+// [N*chunks*groups*2 partials]; ss_groupnorm_ws_floats() sizes it.
+constexpr int GN_TICKETS = 64;
 static inline void groupnorm_geometry(int N, int HW, int C, int* block, int* chunks, int* pix_per_cta) {
   const int vecs = C / 8;
   *block = vecs <= 256 ? vecs * (256 / vecs) : vecs;
@@ -225,7 +240,7 @@ static inline void groupnorm_geometry(int N, int HW, int C, int* block, int* chu
 SS_API int ss_groupnorm_ws_floats(int N, int HW, int C, int groups) {
   int block, chunks, ppc;
   groupnorm_geometry(N, HW, C, &block, &chunks, &ppc);
-  return 2 * N * groups + 2 * N * chunks * groups;
+  return GN_TICKETS + 2 * N * groups + 2 * N * chunks * groups;
 }
 
 SS_API int ss_groupnorm_nhwc(int dtype, const void* x, void* y, const void* gamma, const void* beta, float* stats_ws,
@@ -240,26 +255,24 @@ SS_API int ss_groupnorm_nhwc(int dtype, const void* x, void* y, const void* gamm
   const int vecs = C / 8, nl = block / vecs;
   const size_t smem = (size_t)nl * 2 * C * sizeof(float);
   SS_REQUIRE(smem <= 48 * 1024, "GroupNorm partial kernel shared memory");
-  float* stats = stats_ws;
-  float* partial = stats_ws + 2 * N * groups;
+  SS_REQUIRE(N <= GN_TICKETS, "GroupNorm batch > 64 images");
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(stats_ws);
+  float* stats = stats_ws + GN_TICKETS;
+  float* partial = stats + 2 * N * groups;
   const float inv_cnt = 1.f / ((float)HW * (float)(C / groups));
-  if (dtype == SS_F16)
-    groupnorm_partial_kernel<__half><<<dim3(chunks, N), block, smem, s>>>((const __half*)x, partial, HW, C, groups,
-                                                                        pix_per_cta);
-  else
-    groupnorm_partial_kernel<__nv_bfloat16><<<dim3(chunks, N), block, smem, s>>>((const __nv_bfloat16*)x, partial, HW,
-                                                                               C, groups, pix_per_cta);
-  SS_LAUNCH_CHECK();
-  groupnorm_finalize_kernel<<<ceil_div(N * groups, 4), 128, 0, s>>>(partial, stats, chunks, groups, inv_cnt, eps,
-                                                                   N * groups);
-  SS_LAUNCH_CHECK();
-  if (dtype == SS_F16)
-    groupnorm_apply_kernel<__half><<<dim3(chunks, N), block, 0, s>>>(
-        (const __half*)x, (__half*)y, stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, silu, pix_per_cta);
-  else
-    groupnorm_apply_kernel<__nv_bfloat16><<<dim3(chunks, N), block, 0, s>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, stats, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, HW,
-        C, groups, silu, pix_per_cta);
+  if (dtype == SS_F16) {
+    SS_CUDA(ss::launch_pdl(groupnorm_partial_kernel<__half>, dim3(chunks, N), dim3(block), smem, s, (const __half*)x,
+                           partial, HW, C, groups, pix_per_cta, stats, tickets, inv_cnt, eps));
+    SS_CUDA(ss::launch_pdl(groupnorm_apply_kernel<__half>, dim3(chunks, N), dim3(block), 0, s, (const __half*)x,
+                           (__half*)y, (const float*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, silu,
+                           pix_per_cta));
+  } else {
+    SS_CUDA(ss::launch_pdl(groupnorm_partial_kernel<__nv_bfloat16>, dim3(chunks, N), dim3(block), smem, s,
+                           (const __nv_bfloat16*)x, partial, HW, C, groups, pix_per_cta, stats, tickets, inv_cnt, eps));
+    SS_CUDA(ss::launch_pdl(groupnorm_apply_kernel<__nv_bfloat16>, dim3(chunks, N), dim3(block), 0, s,
+                           (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const float*)stats, (const __nv_bfloat16*)gamma,
+                           (const __nv_bfloat16*)beta, HW, C, groups, silu, pix_per_cta));
+  }
   SS_LAUNCH_CHECK();
   return 0;
 }

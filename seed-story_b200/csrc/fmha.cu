@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(FM_THREADS) fmha_kernel(const FmhaParams p) {
   __half* sK = sQ + 64 * D;       // 2 buffers
   __half* sV = sK + 2 * 64 * D;   // 2 buffers
 
+  pdl_trigger();
+  pdl_wait();  // q/k/v (and kv_lens / page tables) come from preceding kernels
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.x * FM_BM;
@@ -272,7 +274,7 @@ int launch_fmha(const FmhaParams& p, cudaStream_t s) {
     attr = true;
   }
   dim3 grid((p.Lq + FM_BM - 1) / FM_BM, p.H, p.B);
-  fmha_kernel<D, PAGED><<<grid, FM_THREADS, smem, s>>>(p);
+  SS_CUDA(ss::launch_pdl(fmha_kernel<D, PAGED>, grid, dim3(FM_THREADS), (size_t)smem, s, p));
   SS_LAUNCH_CHECK();
   return 0;
 }

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
                                                                 const FtParams p) {
   using S = FtSmem<D>;
   extern __shared__ uint8_t ft_smem_raw[];
+  pdl_trigger();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + S::Q_BYTES;                       // stage s: K at s*2*KV, V right after
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  pdl_wait();  // Q/K/V come from the preceding kernel; O may still be read by an earlier one
   // The whole 512-column TMEM of the SM is allocated (one CTA per SM), so the base is column 0 / lane 0.  Using the
   // constant keeps every TMEM address warp-uniform: with an address loaded from shared memory the compiler wrapped
   // each tcgen05.mma of the single issuing thread in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, and with ~20 small
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_pp_kernel(const __grid_
   constexpr int D = 64;
   using S = FtSmem<D>;
   extern __shared__ uint8_t ft_smem_raw[];
+  pdl_trigger();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + S::Q_BYTES;  // stage s: K at s*2*KV, V right after
@@ -435,6 +438,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_pp_kernel(const __grid_
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  pdl_wait();  // Q/K/V come from the preceding kernel; O may still be read by an earlier one
   if (*tmem_ptr_smem != 0u) __trap();  // all 512 columns are ours: base 0 keeps every TMEM address warp-uniform
   constexpr uint32_t tmem_S0 = 0u, tmem_O = 256u, tmem_L = 384u;
 
@@ -670,12 +674,12 @@ int launch_ft(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& t
       SS_CUDA(cudaFuncSetAttribute(fmha_tc_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     }
     if (pingpong) {
-      fmha_tc_pp_kernel<<<grid, FT_THREADS, S::TOTAL, s>>>(tq, tk, tv, p);
+      SS_CUDA(ss::launch_pdl(fmha_tc_pp_kernel, grid, dim3(FT_THREADS), (size_t)S::TOTAL, s, tq, tk, tv, p));
       SS_LAUNCH_CHECK();
       return 0;
     }
   }
-  fmha_tc_kernel<D><<<grid, FT_THREADS, S::TOTAL, s>>>(tq, tk, tv, p);
+  SS_CUDA(ss::launch_pdl(fmha_tc_kernel<D>, grid, dim3(FT_THREADS), (size_t)S::TOTAL, s, tq, tk, tv, p));
   SS_LAUNCH_CHECK();
   return 0;
 }

@@ -339,7 +339,7 @@ def scatter_rows(src, dst_rows, dst):
 
 def groupnorm_ws(N, HW, C, groups, device):
     n = _capi.lib().ss_groupnorm_ws_floats(N, HW, C, groups)
-    return torch.empty(n, dtype=torch.float32, device=device)
+    return torch.zeros(n, dtype=torch.float32, device=device)   # zero ONCE: the first 64 words are arrival counters
 
 
 def groupnorm_nhwc(x, gamma, beta, groups, eps, silu, stats_ws, out=None):

@@ -201,7 +201,7 @@ class UNetEngine:
 
     # ---- blocks ---------------------------------------------------------------------------------
     def _gn(self, x, wb, eps, silu):
-        self.launches += 3
+        self.launches += 2
         return ops.groupnorm_nhwc(x, wb[0], wb[1], self.groups, eps, silu, self.gn_ws)
 
     def _res(self, r, x):
@@ -362,7 +362,7 @@ class VAEDecoderEngine:
         self.launches = 0
 
     def _gn(self, x, wb, silu):
-        self.launches += 3
+        self.launches += 2
         return ops.groupnorm_nhwc(x, wb[0], wb[1], self.groups, 1e-6, silu, self.gn_ws)
 
     def _res(self, r, x):
