@@ -12,7 +12,7 @@ collective ("scaling": "weak").
 --config sink  (configs[3] shape at batch 1 per GPU): 25-turn stories in LIVE multimodal attention-sink mode (paged KV
 kept across turns, sink retention at every eviction).
 --config sdxl  (configs[4]): a step is one SDXL de-tokenizer image (30 Euler steps, CFG, VAE decode) per GPU from a
-64x4096 image-feature tensor; metric = images/s.
+256x4096 image-feature tensor; metric = images/s.
 
   value : metric with the inputs already on the device, results left on the device
   e2e   : the same steps through the reference-facing API (src.* drop-ins) from HOST buffers: pinned inputs copied H2D
@@ -178,9 +178,9 @@ def run_ours(args):
             torch.cuda.current_stream().synchronize()
             return n
         unit = "story-turns/s"
-    else:   # sdxl standalone: one image per step from a [1, 64, 4096] image-feature tensor (what the MLLM hands over)
+    else:   # sdxl standalone: one image per step from a [1, 256, 4096] image-feature tensor (what the MLLM hands over)
         g = torch.Generator().manual_seed(77 + rank)
-        feats = [(torch.randn(1, 64, 4096, generator=g) * 0.5).half() for _ in range(n_steps_total)]
+        feats = [(torch.randn(1, 256, 4096, generator=g) * 0.5).half() for _ in range(n_steps_total)]
         dev_feats = [f.to(dev) for f in feats]
         pinned_feats = [f.pin_memory() for f in feats]
 
@@ -222,12 +222,14 @@ def run_ours(args):
     value = sum_over_ranks(n_units) / (ms * 1e-3)
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region --------------------------------------
+    # (same steps, same inputs; bounded to args.e2e_steps of them so the whole default run stays within minutes)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
     step_e2e(args.warmup)   # warm the path (pinned allocations)
     counters["h2d"] = counters["d2h"] = 0
     n_units_e2e = 0
     barrier()
     e0.record()
-    for i in range(args.warmup, n_steps_total):
+    for i in range(args.warmup, args.warmup + e2e_steps):
         n_units_e2e += step_e2e(i)
     e1.record()
     barrier()
@@ -248,7 +250,7 @@ def run_ours(args):
                 extra["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
         if args.config == "sdxl":
-            workload = (f"configs[4]: SDXL de-tokenizer standalone, one 1024^2 image per step per GPU from a 64x4096 image-"
+            workload = (f"configs[4]: SDXL de-tokenizer standalone, one 1024^2 image per step per GPU from a 256x4096 image-"
                         f"feature tensor: ResamplerXLV2 + zero-image ViT branch (cached) + {args.denoise_steps} Euler steps CFG 7.5 "
                         f"(UNet batch 2) + VAE decode")
         elif args.config == "sink":
@@ -268,8 +270,9 @@ def run_ours(args):
                                 weights="seeded random, real shapes (no checkpoints offline)",
                                 schedule="EOS and <img> suppressed in the 64 free text slots (SuppressTokens semantics), <img> "
                                          "forced at slot 64, EOS after </img>"),
-                    e2e=dict(value=round(e2e_value, 4), unit=unit, h2d_bytes_per_step=counters["h2d"] // args.steps,
-                             d2h_bytes_per_step=counters["d2h"] // args.steps),
+                    e2e=dict(value=round(e2e_value, 4), unit=unit, h2d_bytes_per_step=counters["h2d"] // e2e_steps,
+                             d2h_bytes_per_step=counters["d2h"] // e2e_steps, steps=e2e_steps,
+                             ms_per_step=round(ms_e2e / e2e_steps, 2)),
                     gpu_launches=int(launches), clocks=clocks)
         line.update(extra)
         print(json.dumps(line))
@@ -390,7 +393,7 @@ def measure_rooflines(pipe, dev, peaks, args):
         achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s", frac=round(gbs / peaks["hbm"], 4),
         algorithmic_bytes=int(wbytes + kvbytes), context=int(mean_ctx), ms=round(dec_ms, 4), peak_source=peaks["src"])
     # ---- SDXL de-tokenizer alone (the img/s half of the metric)
-    feat = (torch.randn(1, 64, 4096, device=dev) * 0.5).half()
+    feat = (torch.randn(1, 256, 4096, device=dev) * 0.5).half()
 
     def one():
         return pipe.adapter.generate(image_embeds=feat, num_inference_steps=args.denoise_steps, height=1024, width=1024,
@@ -651,6 +654,7 @@ def main():
     ap.add_argument("--config", default="story", choices=["story", "sink", "sdxl"])
     ap.add_argument("--turns", type=int, default=None)
     ap.add_argument("--denoise-steps", type=int, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=6, help="steps of the host-buffer (e2e) leg, <= --steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     args = ap.parse_args()

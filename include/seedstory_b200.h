@@ -62,8 +62,24 @@ SS_EXPORT int ss_rope_kv_append_f16(const void* qkv, int ld_qkv, void* q_out, vo
                                     const int* tok_seq, const int* tok_pos, const int* tok_slot, int ntok,
                                     const int* page_table, int max_pages, const void* cos_table,
                                     const void* sin_table, int H, int D, void* stream);
+/* The same projection with LlamaRMSNorm (:107-115, identical rounding chain) recomputed in the kernel prologue:
+ * y = epilogue(RMSNorm(x; gamma, eps) W^T) — input_layernorm -> q/k/v (:341, 228-230) and post_attention_layernorm ->
+ * gate/up (:357-358, 191) of a decode step without a separate normalisation launch.  epilogue: 0 none, 2 SwiGLU. */
+SS_EXPORT int ss_skinny_gemm_rmsnorm_f16(const void* x, int ldx, const void* gamma, float eps, const void* W, void* y,
+                                         int ldy, int B, int N, int K, int epilogue, void* stream);
+/* The attention input side of one decode layer in one launch (LlamaDecoderLayer.forward :341 + LlamaAttention.forward
+ * :228-244): RMSNorm -> q/k/v projection -> apply_rotary_pos_emb -> q to q_out [B, H*D], k (post-RoPE) and v appended
+ * to the paged cache.  Wqkv_il [3*H*D, K] = rows [q | k | v] where inside every q and k head the rows are
+ * pair-interleaved (row 2i = dim i, row 2i+1 = dim i + D/2: a rotary pair sits in neighbouring rows); v rows natural. */
+SS_EXPORT int ss_decode_qkv_rope_append_f16(const void* x, int ldx, const void* gamma, float eps, const void* Wqkv_il,
+                                            void* q_out, void* kcache, void* vcache, const int* tok_seq,
+                                            const int* tok_pos, const int* tok_slot, int B, const int* page_table,
+                                            int max_pages, const void* cos_table, const void* sin_table, int H, int D,
+                                            int K, void* stream);
 /* xops.memory_efficient_attention(q,k,v, LowerTriangularFromBottomRightMask) for q_len == 1 (:289-295)
- * over the pages retained in page_table (window + attention-sink pages). workspace: B*H*splits*(D+2) floats. */
+ * over the pages retained in page_table (window + attention-sink pages); split over pages and merged by the last
+ * CTA to arrive (one launch).  workspace: B*H*splits*(D+2) floats followed by B*H int32 arrival counters that must be
+ * zero before the first call (the kernel leaves them zero). */
 SS_EXPORT int ss_attn_decode_paged_f16(const void* q, const void* kcache, const void* vcache, const int* seq_lens,
                                        const int* page_table, int max_pages, void* out, float* workspace, int B, int H,
                                        int D, int splits, float scale, void* stream);
@@ -119,6 +135,19 @@ SS_EXPORT int ss_kv_scatter_tokens_16b(void* kpool_layer, void* vpool_layer, con
 SS_EXPORT int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N,
                          int K, const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr,
                          int act, int glu, float alpha, int force_bn, int flags, void* stream);
+/* The same GEMM with a LayerNorm folded around it (the LN -> Linear pairs of diffusers' BasicTransformerBlock that
+ * src/models_ipa/adapter_modules.py:455-466 reaches: norm1 -> attn1.to_q/k/v, norm2 -> attn2.to_q, norm3 -> ff.net.0).
+ * Consumer side (ln_stats != NULL): A holds the RAW rows x [M,K], B holds W' = gamma (.) W, and the epilogue evaluates
+ *   LN(x) W^T + b = rstd (x W'^T - mean ln_colsum) + ln_shift,   ln_colsum[n] = sum_k W'[n,k] (fp32),
+ *   ln_shift[n] = sum_k beta[k] W[n,k] + b[n] (fp32); `bias` must be NULL.  mean / rstd of row m are formed from
+ *   ln_slots partial (sum, sum of squares) pairs ln_stats[slot][m][2] (fp32) left by the GEMM that wrote x.
+ * Producer side (stats_out != NULL, non-GLU): this GEMM leaves those partials for ITS output rows (of the values as
+ *   stored, after bias / activation / residual), ss_gemm_row_stat_slots(M, N) slots, layout [slot][M][2] fp32. */
+SS_EXPORT int ss_gemm_tn_ln(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N,
+                            int K, const void* bias, const void* residual, int ldr, int act, int glu, int flags,
+                            const float* ln_stats, int ln_slots, const float* ln_colsum, const float* ln_shift,
+                            float ln_eps, float* stats_out, void* stream);
+SS_EXPORT int ss_gemm_row_stat_slots(int M, int N);
 /* 3x3 / stride 1 / pad 1 convolution on NHWC activations as an implicit GEMM (diffusers ResnetBlock2D
  * conv1/conv2, Up/Downsample convs, VAE decoder convs — SURVEY.md Appendix C).  w is [Cout, 9*Cin] with
  * k = (ky*3+kx)*Cin + c.  bias2 is the per-image time-embedding row [Nimg, Cout]. */

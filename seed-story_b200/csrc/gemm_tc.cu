@@ -20,8 +20,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 bytes = one swizzle row
-constexpr int GEMM_THREADS = 192;          // v1 kernel: 2 + 4 warps
-constexpr int GEMM_PERSIST_THREADS = 320;  // v2 kernel: TMA, MMA + two epilogue groups of 4 warps
+constexpr int GEMM_PERSIST_THREADS = 320;  // TMA, MMA + two epilogue groups of 4 warps
 
 struct GemmParams {
   void* out;
@@ -37,17 +36,19 @@ struct GemmParams {
   float alpha;
   int M, N, K;
   int b_const;  // B is a weight matrix nothing on the stream writes: its first tiles may be fetched before the PDL wait
+  // LayerNorm folded around the GEMM.  Consumer side: A holds the RAW rows x, B holds W' = gamma (.) W, and the
+  // epilogue turns acc = x W'^T into LN(x) W^T + b = rstd (acc - mean colsum) + shift with colsum[n] = sum_k W'[n,k],
+  // shift[n] = sum_k beta[k] W[n,k] + b[n]; mean / rstd of a row come from `ln_slots` partial (sum, sum of squares)
+  // pairs laid out [slot][M] that the GEMM which produced x left behind.  Producer side: stats_out receives those
+  // partials for this GEMM's (rounded) output rows, two slots per N tile.
+  const float* ln_stats;
+  int ln_slots;
+  const float* ln_colsum;
+  const float* ln_shift;
+  float ln_eps;
+  float* stats_out;
   // conv mode
   int H, W, Cin, bw, bh, tiles_x, tiles_y;
-};
-
-template <int BN>
-struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <typename T>
@@ -57,202 +58,6 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
-template <typename T, int BN, bool CONV>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB,
-                                                               const GemmParams p) {
-  using L = SmemLayout<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::STAGES * L::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + L::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + L::STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-
-  // tile coordinates
-  int m0 = 0, img = 0, y0 = 0, x0 = 0;
-  if (CONV) {
-    int t = blockIdx.y;
-    const int tx = t % p.tiles_x;
-    t /= p.tiles_x;
-    const int ty = t % p.tiles_y;
-    img = t / p.tiles_y;
-    y0 = ty * p.bh;
-    x0 = tx * p.bw;
-  } else {
-    m0 = blockIdx.y * BM;
-  }
-  const int kchunks = CONV ? (p.Cin / BK) : ((p.K + BK - 1) / BK);
-  const int num_kb = CONV ? 9 * kchunks : kchunks;
-
-  if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmA);
-    tc::prefetch_tmap(&tmB);
-  }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < L::STAGES; ++s) {
-        tc::mbar_init(&full_bar[s], 1);
-        tc::mbar_init(&empty_bar[s], 1);
-      }
-      tc::mbar_init(tmem_full_bar, 1);
-      tc::fence_barrier_init();
-    }
-    __syncwarp();
-    tc::tmem_alloc(tmem_ptr_smem, BN < 32 ? 32 : BN);
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % L::STAGES;
-        const uint32_t ph = (kb / L::STAGES) & 1;
-        tc::mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        tc::mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        if (CONV) {
-          const int tap = kb / kchunks, c0 = (kb % kchunks) * BK;
-          const int ky = tap / 3, kx = tap % 3;
-          tc::tma_load_4d(sa, &tmA, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, img);
-          tc::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.Cin + c0, n0);
-        } else {
-          tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
-          tc::tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc(sizeof(T) == 2 && !std::is_same<T, __half>::value, BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % L::STAGES;
-        const uint32_t ph = (kb / L::STAGES) & 1;
-        tc::mbar_wait(&full_bar[s], ph);
-        tc::fence_after_sync();
-        const uint32_t sa = tc::smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
-        const uint64_t da = tc::make_desc_sw128(sa);
-        const uint64_t db = tc::make_desc_sw128(sb);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
-          tc::mma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-        }
-        tc::mma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
-      }
-      tc::mma_commit(tmem_full_bar);  // accumulator complete
-    }
-  } else {
-    // ================= epilogue (warps 2..5) =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
-    tc::mbar_wait(tmem_full_bar, 0);
-    tc::fence_after_sync();
-
-    long long m;  // output row
-    bool row_ok;
-    if (CONV) {
-      const int yy = y0 + r / p.bw, xx = x0 + r % p.bw;
-      m = ((long long)img * p.H + yy) * p.W + xx;
-      row_ok = (yy < p.H) && (xx < p.W);
-    } else {
-      m = m0 + r;
-      row_ok = m < p.M;
-    }
-    T* out_row = reinterpret_cast<T*>(p.out) + m * p.ldo;
-    const T* res_row = p.residual ? reinterpret_cast<const T*>(p.residual) + m * p.ldr : nullptr;
-    const T* b2_row =
-        p.bias2 ? reinterpret_cast<const T*>(p.bias2) + (m / p.rows_per_group) * (long long)p.ld_b2 : nullptr;
-
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t raw[32];
-      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
-      tc::tmem_ld_wait();
-      const int col0 = n0 + c;
-      if (!row_ok || col0 >= p.N) continue;
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-      // columns are handled in groups of 8 (16-byte vectors); N % 8 == 0 is required by the host
-#pragma unroll
-      for (int gI = 0; gI < 4; ++gI) {
-        const int col = col0 + gI * 8;
-        if (col >= p.N) break;
-        float* vv = v + gI * 8;
-        if (p.bias) {
-          float bf[8];
-          unpack8<T>(ld_cached16(reinterpret_cast<const T*>(p.bias) + col), bf);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vv[i] += bf[i];
-        }
-        // round to storage precision after every reference-visible op
-#pragma unroll
-        for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i]));
-        if (b2_row) {
-          float bf[8];
-          unpack8<T>(ld_cached16(b2_row + col), bf);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
-        }
-        if (p.glu == 0) {
-          if (p.act) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(act_apply<T>(vv[i], p.act)));
-          }
-          if (res_row) {
-            float rf[8];
-            unpack8<T>(ld_cached16(res_row + col), rf);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] += rf[i];
-          }
-          st16(out_row + col, pack8<T>(vv));
-        } else {
-          // interleaved pairs (first, second) -> 4 outputs per 8 columns
-          T o4[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float a = vv[2 * i], b = vv[2 * i + 1];
-            float o;
-            if (p.glu == 1)
-              o = a * ss_num<T>::to_f(ss_num<T>::from_f(gelu_erf(b)));
-            else
-              o = ss_num<T>::to_f(ss_num<T>::from_f(a / (1.f + expf(-a)))) * b;
-            o4[i] = ss_num<T>::from_f(o);
-          }
-          *reinterpret_cast<uint2*>(out_row + (col >> 1)) = *reinterpret_cast<const uint2*>(o4);
-        }
-      }
-    }
-  }
-
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
-}
-
-
-// =============================================================================================
-// v2: persistent kernel.  One CTA per SM loops over output tiles (n fastest, so consecutive CTAs share the
-// A tile through L2); the TMA->smem ring runs continuously across tiles; TMEM holds TWO accumulators so the
-// MMA of tile i+1 overlaps the epilogue of tile i; the epilogue stages fp16/bf16 rows in swizzled shared
-// memory and writes them with TMA tile stores (full 128-byte lines, bounds clipped by the tensor map).
-// =============================================================================================
-// One accumulator tile (this CTA's 128 rows x BN columns at `taddr`) -> epilogue -> global memory, executed by one
-// epilogue warp (lane quarter q) for the fills f_begin, f_begin + f_step, ...  Shared by the persistent and the
-// CTA-pair kernel.  A fill is 64 output columns staged in 128B-swizzled shared memory and written by a TMA tile
-// store; a 160-wide tile ends in a 32-column tail that is stored straight from registers.
 template <typename T, int BN, bool REMOTE>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tmC, uint8_t* stg, uint32_t taddr,
                                               uint64_t* full_bar, uint32_t full_parity, uint64_t* empty_bar, int n0,
@@ -282,6 +87,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
     }
   };
   if (f_begin < nfills) request(n0 + f_begin * acc_per_fill);
+  // folded LayerNorm, consumer side: this row's mean / rstd from the partial sums its producer left (summed in slot
+  // order: deterministic); fetched while the main loop still runs
+  float ln_a = 1.f, ln_b = 0.f;  // v -> ln_a * v + ln_b * colsum[col] + shift[col]
+  if (p.ln_stats) {
+    float s1 = 0.f, s2 = 0.f;
+    if (row_ok) {
+      const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + m;
+      for (int sl = 0; sl < p.ln_slots; ++sl) {
+        const float2 v2 = st[(size_t)sl * p.M];
+        s1 += v2.x;
+        s2 += v2.y;
+      }
+    }
+    const float inv_k = 1.f / (float)p.K;
+    const float mean = s1 * inv_k;
+    const float var = fmaxf(s2 * inv_k - mean * mean, 0.f);
+    ln_a = rsqrtf(var + p.ln_eps);
+    ln_b = -mean * ln_a;
+  }
+  float st_sum = 0.f, st_sq = 0.f;  // producer side: statistics of this thread's row over the columns it stores
   tc::mbar_wait(full_bar, full_parity);
   tc::fence_after_sync();
 
@@ -333,6 +158,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       for (int gI = 0; gI < 4; ++gI) {
         float* vv = v + gI * 8;
         float bf[8];
+        if (p.ln_stats) {
+          const int col = min(col0 + gI * 8, p.N - 8);
+          const float4* cs = reinterpret_cast<const float4*>(p.ln_colsum + col);
+          const float4* sh = reinterpret_cast<const float4*>(p.ln_shift + col);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const float4 c4 = __ldg(cs + hf), d4 = __ldg(sh + hf);
+            vv[hf * 4 + 0] = fmaf(ln_a, vv[hf * 4 + 0], fmaf(ln_b, c4.x, d4.x));
+            vv[hf * 4 + 1] = fmaf(ln_a, vv[hf * 4 + 1], fmaf(ln_b, c4.y, d4.y));
+            vv[hf * 4 + 2] = fmaf(ln_a, vv[hf * 4 + 2], fmaf(ln_b, c4.z, d4.z));
+            vv[hf * 4 + 3] = fmaf(ln_a, vv[hf * 4 + 3], fmaf(ln_b, c4.w, d4.w));
+          }
+        }
         unpack8<T>(vb[gI], bf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
@@ -350,6 +188,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
             unpack8<T>(vr[gI], bf);
 #pragma unroll
             for (int i = 0; i < 8; ++i) vv[i] += bf[i];
+          }
+          if (p.stats_out && col0 + gI * 8 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float r = ss_num<T>::to_f(ss_num<T>::from_f(vv[i]));  // the value that is stored
+              st_sum += r;
+              st_sq = fmaf(r, r, st_sq);
+            }
           }
           if (direct) {
             if (row_ok && col0 + gI * 8 < p.N) st16(out_row + col0 + gI * 8, pack8<T>(vv));
@@ -394,7 +240,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       tc::tma_store_commit();
     }
   }
+  if (p.stats_out && row_ok) {
+    // two slots per N tile: the two epilogue groups' halves of the tile, or (whole tile by one group) the sums and zeros
+    float2* so = reinterpret_cast<float2*>(p.stats_out) + m;
+    const int slot = (n0 / BN) * 2;
+    if (f_step == 2) {
+      so[(size_t)(slot + f_begin) * p.M] = make_float2(st_sum, st_sq);
+    } else {
+      so[(size_t)slot * p.M] = make_float2(st_sum, st_sq);
+      so[(size_t)(slot + 1) * p.M] = make_float2(0.f, 0.f);
+    }
   }
+}
 
 template <int BN>
 struct PersistLayout {
@@ -869,33 +726,6 @@ int ss_internal_get_tmap(CUtensorMap* out, const void* ptr, int dtype, int rank,
 
 namespace {
 
-template <typename T, int BN, bool CONV>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t s) {
-  using L = SmemLayout<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
-  gemm_tc_kernel<T, BN, CONV><<<grid, GEMM_THREADS, L::TOTAL, s>>>(ta, tb, p);
-  SS_LAUNCH_CHECK();
-  return 0;
-}
-
-template <bool CONV>
-int dispatch(int dtype, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
-             cudaStream_t s) {
-  if (dtype == SS_F16) {
-    if (bn == 64) return launch<__half, 64, CONV>(ta, tb, p, grid, s);
-    if (bn == 128) return launch<__half, 128, CONV>(ta, tb, p, grid, s);
-    return launch<__half, 256, CONV>(ta, tb, p, grid, s);
-  } else {
-    if (bn == 64) return launch<__nv_bfloat16, 64, CONV>(ta, tb, p, grid, s);
-    if (bn == 128) return launch<__nv_bfloat16, 128, CONV>(ta, tb, p, grid, s);
-    return launch<__nv_bfloat16, 256, CONV>(ta, tb, p, grid, s);
-  }
-}
-
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -905,15 +735,6 @@ int sm_count() {
     if (n <= 0) n = 148;
   }
   return n;
-}
-
-bool use_legacy() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SS_GEMM_LEGACY");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
 }
 
 template <typename T, int BN, bool CONV>
@@ -1082,39 +903,39 @@ int get_out_tmap(CUtensorMap* out, const void* C, int dtype, long long M, int n_
   return get_tmap(out, C, dtype, 2, dims, str, box);
 }
 
-int pick_bn(long long m_tiles, int N, int force_bn) {
-  if (force_bn == 64 || force_bn == 128 || force_bn == 256) return force_bn;
-  if (N <= 64) return 64;
-  const long long t256 = m_tiles * ((N + 255) / 256), t128 = m_tiles * ((N + 127) / 128);
-  if (N >= 256 && t256 >= 2 * 148) return 256;
-  if (t128 >= 148) return 128;
-  return 64;
-}
-
 }  // namespace
 
-// C[M,N] = epi(alpha * A[M,K] B[N,K]^T); see include/seedstory_b200.h for the argument contract.
-SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
-                      const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr, int act,
-                      int glu, float alpha, int force_bn, int flags, void* stream) {
+// Row-statistics slots a GEMM with `stats_out` writes per output row: two per N tile of the kernel the dispatcher
+// picks for this shape (one per epilogue group).
+static int stat_slots_for(long long m_tiles, int N, int glu, int force_bn) {
+  if (const int pbn = pick_pair(m_tiles, N, glu, force_bn)) return 2 * ((N + pbn - 1) / pbn);
+  const int bn = pick_bn_persist(m_tiles, N, glu, force_bn);
+  return 2 * ((N + bn - 1) / bn);
+}
+
+SS_API int ss_gemm_row_stat_slots(int M, int N) {
+  return stat_slots_for((M + BM - 1) / BM, N, 0, 0);
+}
+
+static int gemm_tn_impl(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                        const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr, int act,
+                        int glu, float alpha, int force_bn, int flags, const float* ln_stats, int ln_slots,
+                        const float* ln_colsum, const float* ln_shift, float ln_eps, float* stats_out, void* stream) {
   SS_REQUIRE(dtype == SS_F16 || dtype == SS_BF16, "dtype must be f16 or bf16");
   SS_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
   SS_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "N, K, lda, ldb, ldc % 8");
   SS_REQUIRE(glu == 0 || (act == 0 && residual == nullptr), "GLU epilogue excludes act/residual");
   SS_REQUIRE(bias2 == nullptr || rows_per_group > 0, "bias2 needs rows_per_group");
+  SS_REQUIRE(ln_stats == nullptr || (ln_slots > 0 && ln_colsum && ln_shift && bias == nullptr && bias2 == nullptr),
+             "folded LayerNorm needs slots, colsum and shift, and carries the bias inside `shift`");
+  SS_REQUIRE(stats_out == nullptr || glu == 0, "row statistics are produced by non-GLU epilogues");
   const long long m_tiles = (M + BM - 1) / BM;
-  const bool legacy = use_legacy();
-  const int bn = legacy ? pick_bn(m_tiles, N, force_bn) : pick_bn_persist(m_tiles, N, glu, force_bn);
+  const int bn = pick_bn_persist(m_tiles, N, glu, force_bn);
   CUtensorMap ta, tb;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)lda * 2};
     uint32_t box[2] = {BK, BM};
     if (int e = get_tmap(&ta, A, dtype, 2, dims, str, box)) return e;
-  }
-  {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {BK, (uint32_t)bn};
-    if (int e = get_tmap(&tb, B, dtype, 2, dims, str, box)) return e;
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -1133,23 +954,48 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
   p.N = N;
   p.K = K;
   p.b_const = (flags & 1 /* SS_GEMM_B_CONST */) ? 1 : 0;
-  if (!legacy) {
-    CUtensorMap tcm;
-    if (int e = get_out_tmap(&tcm, C, dtype, M, glu ? N / 2 : N, ldc)) return e;
-    if (const int pbn = pick_pair(m_tiles, N, glu, force_bn)) {
-      CUtensorMap tb2;
-      uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)ldb * 2};
-      uint32_t box[2] = {BK, (uint32_t)pbn / 2};
-      if (int e = get_tmap(&tb2, B, dtype, 2, dims, str, box)) return e;
-      const int n_tiles_n = (N + pbn - 1) / pbn;
-      const long long pair_tiles = ((m_tiles + 1) / 2) * n_tiles_n;
-      return dispatch_pair<false>(dtype, pbn, ta, tb2, tcm, p, n_tiles_n, pair_tiles, (cudaStream_t)stream);
-    }
-    const int n_tiles_n = (N + bn - 1) / bn;
-    return dispatch_persist<false>(dtype, bn, ta, tb, tcm, p, n_tiles_n, m_tiles * n_tiles_n, (cudaStream_t)stream);
+  p.ln_stats = ln_stats;
+  p.ln_slots = ln_slots;
+  p.ln_colsum = ln_colsum;
+  p.ln_shift = ln_shift;
+  p.ln_eps = ln_eps;
+  p.stats_out = stats_out;
+  CUtensorMap tcm;
+  if (int e = get_out_tmap(&tcm, C, dtype, M, glu ? N / 2 : N, ldc)) return e;
+  if (const int pbn = pick_pair(m_tiles, N, glu, force_bn)) {
+    CUtensorMap tb2;
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)ldb * 2};
+    uint32_t box[2] = {BK, (uint32_t)pbn / 2};
+    if (int e = get_tmap(&tb2, B, dtype, 2, dims, str, box)) return e;
+    const int n_tiles_n = (N + pbn - 1) / pbn;
+    const long long pair_tiles = ((m_tiles + 1) / 2) * n_tiles_n;
+    return dispatch_pair<false>(dtype, pbn, ta, tb2, tcm, p, n_tiles_n, pair_tiles, (cudaStream_t)stream);
   }
-  dim3 grid((N + bn - 1) / bn, (unsigned)m_tiles);
-  return dispatch<false>(dtype, bn, ta, tb, p, grid, (cudaStream_t)stream);
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)ldb * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    if (int e = get_tmap(&tb, B, dtype, 2, dims, str, box)) return e;
+  }
+  const int n_tiles_n = (N + bn - 1) / bn;
+  return dispatch_persist<false>(dtype, bn, ta, tb, tcm, p, n_tiles_n, m_tiles * n_tiles_n, (cudaStream_t)stream);
+}
+
+// C[M,N] = epi(alpha * A[M,K] B[N,K]^T); see include/seedstory_b200.h for the argument contract.
+SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                      const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr, int act,
+                      int glu, float alpha, int force_bn, int flags, void* stream) {
+  return gemm_tn_impl(dtype, A, lda, B, ldb, C, ldc, M, N, K, bias, bias2, rows_per_group, residual, ldr, act, glu, alpha,
+                      force_bn, flags, nullptr, 0, nullptr, nullptr, 0.f, nullptr, stream);
+}
+
+// The same GEMM with a LayerNorm folded around it (include/seedstory_b200.h): `ln_*` apply LN to A's rows from row
+// statistics an earlier GEMM left in `ln_stats`; `stats_out` makes THIS GEMM leave the statistics of its output rows.
+SS_API int ss_gemm_tn_ln(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                         const void* bias, const void* residual, int ldr, int act, int glu, int flags,
+                         const float* ln_stats, int ln_slots, const float* ln_colsum, const float* ln_shift, float ln_eps,
+                         float* stats_out, void* stream) {
+  return gemm_tn_impl(dtype, A, lda, B, ldb, C, ldc, M, N, K, bias, nullptr, 0, residual, ldr, act, glu, 1.f, 0, flags,
+                      ln_stats, ln_slots, ln_colsum, ln_shift, ln_eps, stats_out, stream);
 }
 
 // 3x3 stride-1 pad-1 convolution, NHWC activations [Nimg,H,W,Cin], weights [Cout, 9*Cin] with
@@ -1163,8 +1009,7 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
   int bw = W >= 128 ? 128 : W, bh = BM / bw;
   SS_REQUIRE(bw * bh == BM && W % bw == 0 && H % bh == 0, "image must tile into 128-pixel boxes");
   const long long m_tiles = (long long)Nimg * (H / bh) * (W / bw);
-  const bool legacy = use_legacy();
-  const int bn = legacy ? pick_bn(m_tiles, Cout, force_bn) : pick_bn_persist(m_tiles, Cout, 0, force_bn);
+  const int bn = pick_bn_persist(m_tiles, Cout, 0, force_bn);
   CUtensorMap ta, tb;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
@@ -1200,7 +1045,7 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
   p.bh = bh;
   p.tiles_x = W / bw;
   p.tiles_y = H / bh;
-  if (!legacy) {
+  {
     CUtensorMap tcm;
     if (int e = get_out_tmap(&tcm, y, dtype, (long long)Nimg * H * W, Cout, Cout)) return e;
     if (const int pbn = pick_pair(m_tiles, Cout, 0, force_bn)) {
@@ -1215,6 +1060,4 @@ SS_API int ss_conv3x3_nhwc(int dtype, const void* x, const void* w, void* y, int
     const int n_tiles_n = (Cout + bn - 1) / bn;
     return dispatch_persist<true>(dtype, bn, ta, tb, tcm, p, n_tiles_n, m_tiles * n_tiles_n, (cudaStream_t)stream);
   }
-  dim3 grid((Cout + bn - 1) / bn, (unsigned)m_tiles);
-  return dispatch<true>(dtype, bn, ta, tb, p, grid, (cudaStream_t)stream);
 }

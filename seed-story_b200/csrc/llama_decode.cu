@@ -11,11 +11,17 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // skinny GEMM
 // ---------------------------------------------------------------------------------------------
-enum { EPI_NONE = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2 };
+enum { EPI_NONE = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_ROPE_APPEND = 3 };
+constexpr int KV_PAGE = 64;
+
+__device__ __forceinline__ __half hadd_t(__half a, __half b) {  // torch's half add: fp32 add, one rounding
+  return __float2half_rn(__half2float(a) + __half2float(b));
+}
 
 __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
@@ -28,23 +34,50 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
 constexpr int SG_WARPS_MAX = 8;
 constexpr int SG_UNROLL = 8;   // k-blocks (32 wide) per register batch; two batches are in flight per warp
 constexpr int SG_ROWS = 8;     // weight rows per CTA
+constexpr int SG_XS_PAD = 32;  // halves of padding per staged activation row (64 B: rows land in alternate bank halves)
+
+// Fused prologue / epilogue operands of the decode-layer kernels (all device pointers).
+struct SkinnyFuse {
+  // NORM prologue: x is the raw residual-stream row; the CTA recomputes LlamaRMSNorm (modeling_llama_xformer.py:107-115,
+  // same rounding chain and the same reduction order as rmsnorm_f16_kernel) into shared memory before the dot products
+  const __half* gamma;
+  float eps;
+  // EPI_ROPE_APPEND: W rows of the q and k sections are stored pair-interleaved per head (row 2i = dim i, row 2i+1 =
+  // dim i + D/2), so the two halves of a rotary pair are neighbours in the CTA's 8 output rows
+  __half* q_out;         // [B, H*D] natural order
+  __half* kcache;        // this layer's K pages [page][H][64][D]
+  __half* vcache;
+  const int* tok_seq;
+  const int* tok_pos;
+  const int* tok_slot;
+  const int* page_table;
+  int max_pages;
+  const __half* cos_t;   // [max_pos, D] fp16
+  const __half* sin_t;
+  int H, D;
+};
 
 // One CTA = 8 rows of W.  The weight rows are the B operand (n = row), the <= 8 activation rows the A operand
 // (m = batch index, rows 8..15 zero), so a lane streams ONE 16-byte piece of one weight row per 32-wide k-block;
 // the 8 warps interleave over k-blocks, keep two register batches of loads in flight (software pipeline) and
 // reduce their 8x8 partial results through shared memory.
-template <int EPI, int SG_WARPS>
+template <int EPI, int SG_WARPS, bool NORM>
 __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half* __restrict__ x, int ldx,
                                                                     const __half* __restrict__ W,
                                                                     __half* __restrict__ y, int ldy, int B, int N,
-                                                                    int K, const __half* __restrict__ res, int ldr) {
+                                                                    int K, const __half* __restrict__ res, int ldr,
+                                                                    const SkinnyFuse fz) {
   __shared__ float part[SG_WARPS_MAX][8][8];  // [warp][batch][row]
+  __shared__ float red[32];
+  extern __shared__ __align__(16) uint8_t sg_dyn[];
+  __half* xs = reinterpret_cast<__half*>(sg_dyn);  // NORM: [B][K + SG_XS_PAD] normalised activations
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * SG_ROWS;
   const int r_w = min(row0 + g, N - 1);  // clamp: tail rows are recomputed, never stored
   const __half* wp = W + (size_t)r_w * K + t * 8;
-  const __half* xg = x + (size_t)min(g, B - 1) * ldx + t * 8;
+  const int xs_ld = K + SG_XS_PAD;
+  const __half* xg = NORM ? (xs + (size_t)min(g, B - 1) * xs_ld + t * 8) : (x + (size_t)min(g, B - 1) * ldx + t * 8);
   const bool xvalid = g < B;
   const int nkb = K >> 5;
   const int my_n = (nkb - warp + SG_WARPS - 1) / SG_WARPS;  // k-blocks owned by this warp: warp, warp+8, ...
@@ -64,7 +97,11 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
 #pragma unroll
     for (int u = 0; u < SG_UNROLL; ++u) {
       const int i = first + u;
-      xb[u] = (xvalid && i < my_n) ? ld_cached16(xg + ((size_t)(warp + i * SG_WARPS) << 5)) : vec8{0u, 0u, 0u, 0u};
+      if (NORM)
+        xb[u] = (xvalid && i < my_n) ? *reinterpret_cast<const vec8*>(xg + ((size_t)(warp + i * SG_WARPS) << 5))
+                                     : vec8{0u, 0u, 0u, 0u};
+      else
+        xb[u] = (xvalid && i < my_n) ? ld_cached16(xg + ((size_t)(warp + i * SG_WARPS) << 5)) : vec8{0u, 0u, 0u, 0u};
     }
 #pragma unroll
     for (int u = 0; u < SG_UNROLL; ++u) {
@@ -75,6 +112,35 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
   };
   load_batch(wa, 0);  // weights are constants: in flight before we wait for the producer of x
   pdl_wait();
+  if (NORM) {
+    // RMSNorm of the <= 8 activation rows, recomputed per CTA (8 KB per row out of L2) while the first weight batch
+    // is in flight; arithmetic and reduction order are those of rmsnorm_f16_kernel (256 threads, pieces tid, tid+256..)
+    const int nvec = K >> 3;
+    for (int b = 0; b < B; ++b) {
+      const __half* xr = x + (size_t)b * ldx;
+      float ss = 0.f;
+      for (int vi = threadIdx.x; vi < nvec; vi += SG_WARPS * 32) {
+        float f[8];
+        unpack8<__half>(ld_cached16(xr + vi * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+      }
+      ss = block_sum(ss, red);
+      const float rstd = __frsqrt_rn(ss / (float)K + fz.eps);
+      for (int vi = threadIdx.x; vi < nvec; vi += SG_WARPS * 32) {
+        float f[8];
+        unpack8<__half>(ld_cached16(xr + vi * 8), f);
+        vec8 wv = ld_cached16(fz.gamma + vi * 8);
+        const __half* wh = reinterpret_cast<const __half*>(&wv);
+        vec8 o;
+        __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) oh[j] = __hmul(wh[j], __float2half_rn(f[j] * rstd));
+        *reinterpret_cast<vec8*>(xs + (size_t)b * xs_ld + vi * 8) = o;
+      }
+    }
+    __syncthreads();
+  }
   for (int first = 0; first < my_n; first += 2 * SG_UNROLL) {
     load_batch(wb, first + SG_UNROLL);
     compute_batch(wa, first);
@@ -105,6 +171,40 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
         y[(size_t)n * ldy + out_col] = __hmul(act, __float2half_rn(up));
       }
     }
+  } else if (EPI == EPI_ROPE_APPEND) {
+    // q/k/v projection of one decode token per sequence + apply_rotary_pos_emb (:165-173) + cache append (:241-242):
+    // thread (n, r) owns output row row0 + r of sequence n; rows (2i, 2i+1) of a q/k head are the rotary pair
+    // (d, d + D/2), so the partner value is one lane away.  Same fp16 arithmetic as rope_append_kernel.
+    if (threadIdx.x < 64) {
+      const int n = threadIdx.x >> 3, r = threadIdx.x & 7;
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < SG_WARPS; ++w) acc += part[w][n][r];
+      const __half o = __float2half_rn(acc);
+      const __half other = __ushort_as_half(__shfl_xor_sync(0xffffffffu, __half_as_ushort(o), 1));
+      const int row = row0 + r;
+      const int HD = fz.H * fz.D, half_d = fz.D >> 1;
+      if (n < B && row < N) {
+        const int sec = row / HD, within = row - sec * HD;
+        const int h = within / fz.D, p = within - h * fz.D;
+        const int seq = fz.tok_seq[n], pos = fz.tok_pos[n], slot = fz.tok_slot[n];
+        const int page = fz.page_table[(size_t)seq * fz.max_pages + slot / KV_PAGE];
+        const size_t dst = (((size_t)page * fz.H + h) * KV_PAGE + (slot % KV_PAGE)) * fz.D;
+        if (sec == 2) {
+          fz.vcache[dst + p] = o;  // v rows keep their natural order
+        } else {
+          const int d = (p >> 1) + (p & 1) * half_d;
+          const __half cs = fz.cos_t[(size_t)pos * fz.D + d], sn = fz.sin_t[(size_t)pos * fz.D + d];
+          // d < D/2: x_d cos_d + (-x_{d+D/2}) sin_d ;  d >= D/2: x_d cos_d + x_{d-D/2} sin_d
+          const __half v = (p & 1) ? hadd_t(__hmul(o, cs), __hmul(other, sn))
+                                   : hadd_t(__hmul(o, cs), __hmul(__hneg(other), sn));
+          if (sec == 0)
+            fz.q_out[(size_t)n * HD + h * fz.D + d] = v;
+          else
+            fz.kcache[dst + d] = v;
+        }
+      }
+    }
   } else {
     if (threadIdx.x < 64) {
       const int n = threadIdx.x >> 3, r = threadIdx.x & 7;
@@ -121,45 +221,100 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
   }
 }
 
+template <int EPI, bool NORM>
+static int skinny_launch(const __half* xp, int ldx, const __half* Wp, __half* yp, int ldy, int B, int N, int K,
+                         const __half* rp, int ldr, const SkinnyFuse& fz, cudaStream_t s) {
+  static int warps = 0;
+  if (warps == 0) {
+    const char* e = getenv("SS_SKINNY_WARPS");
+    warps = (e && atoi(e) == 4 && !NORM) ? 4 : 8;   // the NORM prologue reproduces rmsnorm_f16_kernel's 256-thread reduction
+  }
+  const int grid = ceil_div(N, SG_ROWS);
+  const size_t smem = NORM ? (size_t)B * (K + SG_XS_PAD) * sizeof(__half) : 0;
+  if (warps == 4) {
+    auto k = skinny_gemm_kernel<EPI, 4, NORM>;
+    SS_CUDA(ss::launch_pdl(k, dim3(grid), dim3(128), smem, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr, fz));
+  } else {
+    auto k = skinny_gemm_kernel<EPI, 8, NORM>;
+    if (smem > 48 * 1024) {
+      static bool raised = false;
+      if (!raised) {
+        SS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + SG_XS_PAD) * 2));
+        raised = true;
+      }
+    }
+    SS_CUDA(ss::launch_pdl(k, dim3(grid), dim3(256), smem, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr, fz));
+  }
+  SS_LAUNCH_CHECK();
+  return 0;
+}
+
 SS_API int ss_skinny_gemm_f16(const void* x, int ldx, const void* W, void* y, int ldy, int B, int N, int K,
                               int epilogue, const void* residual, int ldr, void* stream) {
   SS_REQUIRE(B >= 1 && B <= 8, "skinny GEMM handles 1..8 rows");
   SS_REQUIRE(K % 32 == 0 && ldx % 8 == 0, "K must be a multiple of 32, ldx of 8");
   SS_REQUIRE(epilogue != EPI_SWIGLU || N % 8 == 0, "SwiGLU needs N % 8 == 0");
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = ceil_div(N, SG_ROWS);
-  static int warps = 0;
-  if (warps == 0) {
-    const char* e = getenv("SS_SKINNY_WARPS");
-    warps = (e && atoi(e) == 4) ? 4 : 8;
-  }
   const __half *xp = (const __half*)x, *Wp = (const __half*)W, *rp = (const __half*)residual;
   __half* yp = (__half*)y;
+  SkinnyFuse fz = {};
   switch (epilogue) {
     case EPI_NONE:
-      if (warps == 4)
-        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_NONE, 4>, dim3(grid), dim3(128), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
-      else
-        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_NONE, 8>, dim3(grid), dim3(256), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
-      break;
+      return skinny_launch<EPI_NONE, false>(xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr, fz, s);
     case EPI_RESIDUAL:
       SS_REQUIRE(residual != nullptr, "residual epilogue needs a residual pointer");
-      if (warps == 4)
-        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_RESIDUAL, 4>, dim3(grid), dim3(128), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
-      else
-        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_RESIDUAL, 8>, dim3(grid), dim3(256), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
-      break;
+      return skinny_launch<EPI_RESIDUAL, false>(xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr, fz, s);
     case EPI_SWIGLU:
-      if (warps == 4)
-        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_SWIGLU, 4>, dim3(grid), dim3(128), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
-      else
-        SS_CUDA(ss::launch_pdl(skinny_gemm_kernel<EPI_SWIGLU, 8>, dim3(grid), dim3(256), 0, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr));
-      break;
+      return skinny_launch<EPI_SWIGLU, false>(xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr, fz, s);
     default:
       SS_FAIL("unknown epilogue");
   }
-  SS_LAUNCH_CHECK();
-  return 0;
+}
+
+// RMSNorm fused into the projection that consumes it: y = epilogue(LlamaRMSNorm(x; gamma, eps) W^T)
+// (input_layernorm -> q/k/v, post_attention_layernorm -> gate/up: modeling_llama_xformer.py:341-359).
+SS_API int ss_skinny_gemm_rmsnorm_f16(const void* x, int ldx, const void* gamma, float eps, const void* W, void* y,
+                                      int ldy, int B, int N, int K, int epilogue, void* stream) {
+  SS_REQUIRE(B >= 1 && B <= 8, "skinny GEMM handles 1..8 rows");
+  SS_REQUIRE(K % 32 == 0 && ldx % 8 == 0 && K <= 8192, "K must be a multiple of 32 (<= 8192), ldx of 8");
+  SS_REQUIRE(epilogue == EPI_NONE || (epilogue == EPI_SWIGLU && N % 8 == 0), "epilogue must be none or SwiGLU (N % 8 == 0)");
+  SkinnyFuse fz = {};
+  fz.gamma = (const __half*)gamma;
+  fz.eps = eps;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (epilogue == EPI_SWIGLU)
+    return skinny_launch<EPI_SWIGLU, true>((const __half*)x, ldx, (const __half*)W, (__half*)y, ldy, B, N, K, nullptr, 0, fz, s);
+  return skinny_launch<EPI_NONE, true>((const __half*)x, ldx, (const __half*)W, (__half*)y, ldy, B, N, K, nullptr, 0, fz, s);
+}
+
+// The attention input side of a decode layer in ONE launch: input RMSNorm -> q/k/v projection -> rotary embedding
+// -> q to q_out, k (post-RoPE) and v appended to the paged cache (modeling_llama_xformer.py:341, 228-244).
+// Wqkv_il: [3*H*D, K]; inside every q and k head the rows are pair-interleaved (row 2i = dim i, 2i+1 = dim i + D/2).
+SS_API int ss_decode_qkv_rope_append_f16(const void* x, int ldx, const void* gamma, float eps, const void* Wqkv_il,
+                                         void* q_out, void* kcache, void* vcache, const int* tok_seq,
+                                         const int* tok_pos, const int* tok_slot, int B, const int* page_table,
+                                         int max_pages, const void* cos_table, const void* sin_table, int H, int D,
+                                         int K, void* stream) {
+  SS_REQUIRE(B >= 1 && B <= 8, "decode handles 1..8 sequences");
+  SS_REQUIRE(K % 32 == 0 && ldx % 8 == 0 && K <= 8192, "K must be a multiple of 32 (<= 8192), ldx of 8");
+  SS_REQUIRE(D % 8 == 0 && D <= 256, "head dim must be a multiple of 8 and <= 256");
+  SkinnyFuse fz = {};
+  fz.gamma = (const __half*)gamma;
+  fz.eps = eps;
+  fz.q_out = (__half*)q_out;
+  fz.kcache = (__half*)kcache;
+  fz.vcache = (__half*)vcache;
+  fz.tok_seq = tok_seq;
+  fz.tok_pos = tok_pos;
+  fz.tok_slot = tok_slot;
+  fz.page_table = page_table;
+  fz.max_pages = max_pages;
+  fz.cos_t = (const __half*)cos_table;
+  fz.sin_t = (const __half*)sin_table;
+  fz.H = H;
+  fz.D = D;
+  return skinny_launch<EPI_ROPE_APPEND, true>((const __half*)x, ldx, (const __half*)Wqkv_il, nullptr, 0, B, 3 * H * D, K,
+                                              nullptr, 0, fz, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -170,12 +325,6 @@ SS_API int ss_skinny_gemm_f16(const void* x, int ldx, const void* W, void* y, in
 //   q_out [ntok, H*D]
 //   K/V cache pages: [page][H][PAGE][D]
 // ---------------------------------------------------------------------------------------------
-constexpr int KV_PAGE = 64;
-
-__device__ __forceinline__ __half hadd_t(__half a, __half b) {  // torch's half add: fp32 add, one rounding
-  return __float2half_rn(__half2float(a) + __half2float(b));
-}
-
 // grid (ntok, H): one CTA per (token, head), D/2 threads: thread d owns the pair (d, d + D/2)
 __global__ void __launch_bounds__(128) rope_append_kernel(const __half* __restrict__ qkv, int ld_qkv,
                                                           __half* __restrict__ q_out, __half* __restrict__ kcache,
@@ -225,158 +374,186 @@ SS_API int ss_rope_kv_append_f16(const void* qkv, int ld_qkv, void* q_out, void*
 }
 
 // ---------------------------------------------------------------------------------------------
-// Paged decode attention, D = 128, one query token per sequence.
-// grid (H, B, S): split s of sequence b handles pages [s*pps, (s+1)*pps) where pps is derived from
-// the device-side sequence length, so the launch is CUDA-graph replayable while lengths grow.
+// Paged decode attention, D = 128, one query token per sequence (HBM-bound: K and V pages are streamed once).
+// grid (H, B, S): CTA s of (head h, sequence b) takes pages s, s+S, ... of the sequence (lengths are read on the
+// device, so the launch is CUDA-graph replayable while sequences grow).  Per 64-token page every thread issues its 8
+// K and 8 V 16-byte loads BEFORE any arithmetic — one memory latency per page instead of one per pass — and the
+// eight half-warps (one key row = 16 lanes x 16 bytes) keep private running maxima / sums / output rows, merged once
+// at the end, so the page loop has no block-wide barrier.  The last CTA of a (b, h) to arrive (device counter)
+// merges the S partial results: split and combine are ONE launch.
 // ---------------------------------------------------------------------------------------------
 constexpr int AD_THREADS = 128;
-constexpr int AD_MAX_CHUNK = 1024;  // tokens per split upper bound (16 pages)
+constexpr int AD_GROUPS = AD_THREADS / 16;  // half-warps
+constexpr int AD_STAGES = 2;
+constexpr int AD_PAGE_BYTES = KV_PAGE * 128 * 2;                 // one head's K (or V) rows of a page: 16 KB, contiguous
+constexpr int AD_SMEM = AD_STAGES * 2 * AD_PAGE_BYTES + 128;     // K + V per stage, + alignment slack
 
-__global__ void __launch_bounds__(AD_THREADS) attn_decode_split_kernel(
+__global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
     const __half* __restrict__ q, const __half* __restrict__ kcache, const __half* __restrict__ vcache,
     const int* __restrict__ seq_lens, const int* __restrict__ page_table, int max_pages, float* __restrict__ part,
-    int H, int S, float scale) {
+    int* __restrict__ counters, __half* __restrict__ out, int H, int S, float scale) {
   constexpr int D = 128;
-  __shared__ float sc[AD_MAX_CHUNK];
-  __shared__ float red[32];
-  __shared__ __align__(16) __half qs[D];
+  extern __shared__ uint8_t ad_dyn[];
+  __shared__ float osm[AD_GROUPS][D + 4];
+  __shared__ float gm[AD_GROUPS], gl[AD_GROUPS];
+  __shared__ __align__(8) uint64_t full_bar[AD_STAGES];
+  __shared__ int last_flag;
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ad_dyn) + 127) & ~uintptr_t(127));
   pdl_trigger();
-  pdl_wait();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AD_STAGES; ++i) tc::mbar_init(&full_bar[i], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();  // q and the newest K/V row come from the preceding kernel
   const int h = blockIdx.x, b = blockIdx.y, s = blockIdx.z;
   const int n = seq_lens[b];
   const int npages = (n + KV_PAGE - 1) / KV_PAGE;
-  const int pps = (npages + S - 1) / S;  // pages per split
-  const int p0 = s * pps, p1 = min(npages, p0 + pps);
-  float* out = part + (((size_t)b * H + h) * S + s) * (D + 2);
-  if (p0 >= p1) {
-    if (threadIdx.x == 0) {
-      out[D] = -INFINITY;
-      out[D + 1] = 0.f;
-    }
-    out[threadIdx.x] = 0.f;
-    return;
-  }
-  const int t0 = p0 * KV_PAGE, t1 = min(n, p1 * KV_PAGE), cnt = t1 - t0;
-  if (threadIdx.x < D) qs[threadIdx.x] = q[((size_t)b * H + h) * D + threadIdx.x];
-  __syncthreads();
-
-  // phase 1: scores. 16 lanes x 16 bytes cover one 256-byte key row; a warp does 2 tokens per iteration.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane >> 4, l16 = lane & 15;
-  float qf[8];
-  unpack8<__half>(*reinterpret_cast<const vec8*>(qs + l16 * 8), qf);
-  // the split's page ids (<= 16) are staged once: the per-token lookup is then a shared-memory read instead of a
-  // dependent global load in front of every K / V row
-  __shared__ int pg[AD_MAX_CHUNK / KV_PAGE];
-  if (threadIdx.x < p1 - p0) pg[threadIdx.x] = page_table[(size_t)b * max_pages + p0 + threadIdx.x];
-  __syncthreads();
-  float lmax = -INFINITY;
-  // warp-uniform trip count (the half-warp shuffles need all 32 lanes converged); four passes of 8 tokens are
-  // batched so that every lane has four independent 16-byte K loads in flight — with one load per pass the loop
-  // paid a full HBM latency per 8 tokens (20 us per layer at ctx 1041 against 2.6 us of traffic)
-  constexpr int PASS = (AD_THREADS / 32) * 2;
-  for (int jb = warp * 2; jb < cnt; jb += PASS * 4) {
-    vec8 kv[4];
+  const int grp = warp * 2 + sub;
+  float* my_part = part + (((size_t)b * H + h) * S + s) * (D + 2);
+
+  if (s < npages) {
+    const int my_pages = (npages - s + S - 1) / S;  // pages s, s+S, ...
+    // page `it` of this CTA -> stage it % AD_STAGES: both the K and the V rows of the page arrive as two bulk copies
+    auto issue = [&](int it) {
+      const int pi = s + it * S;
+      const int page = page_table[(size_t)b * max_pages + pi];
+      const int cnt = min(KV_PAGE, n - pi * KV_PAGE);
+      const uint32_t bytes = (uint32_t)cnt * D * 2;
+      uint8_t* st = stage_base + (it % AD_STAGES) * 2 * AD_PAGE_BYTES;
+      uint64_t* bar = &full_bar[it % AD_STAGES];
+      tc::mbar_expect_tx(bar, 2 * bytes);
+      tc::bulk_load_1d(st, kcache + ((size_t)page * H + h) * KV_PAGE * D, bytes, bar);
+      tc::bulk_load_1d(st + AD_PAGE_BYTES, vcache + ((size_t)page * H + h) * KV_PAGE * D, bytes, bar);
+    };
+    if (threadIdx.x == 0)
+      for (int it = 0; it < min(AD_STAGES, my_pages); ++it) issue(it);
+    float qf[8];
+    unpack8<__half>(ld_cached16(q + ((size_t)b * H + h) * D + l16 * 8), qf);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = jb + u * PASS + sub;
-      const int jj = j < cnt ? j : 0;
-      const int page = pg[jj / KV_PAGE];  // t0 is page aligned
-      kv[u] = ld_stream_rw16(kcache + (((size_t)page * H + h) * KV_PAGE + (jj % KV_PAGE)) * D + l16 * 8);
+    for (int i = 0; i < 8; ++i) qf[i] *= scale;
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int it = 0; it < my_pages; ++it) {
+      const int pi = s + it * S;
+      const int cnt = min(KV_PAGE, n - pi * KV_PAGE);
+      const uint8_t* st = stage_base + (it % AD_STAGES) * 2 * AD_PAGE_BYTES;
+      tc::mbar_wait(&full_bar[it % AD_STAGES], (it / AD_STAGES) & 1);
+      const __half* ks = reinterpret_cast<const __half*>(st) + l16 * 8;
+      const __half* vs = reinterpret_cast<const __half*>(st + AD_PAGE_BYTES) + l16 * 8;
+      float sc[8], pm = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = u * AD_GROUPS + grp;  // token of this half-warp in pass u
+        float kf[8];
+        unpack8<__half>(*reinterpret_cast<const vec8*>(ks + j * D), kf);
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d += qf[i] * kf[i];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        sc[u] = (j < cnt) ? d : -INFINITY;   // rows >= cnt of the stage hold stale bytes
+        pm = fmaxf(pm, sc[u]);
+      }
+      if (pm > -INFINITY) {  // (uniform per half-warp; the shuffles above ran converged)
+        const float mn = fmaxf(m, pm);
+        const float corr = __expf(m - mn);  // m = -inf on the first page: exp(-inf) = 0
+        l *= corr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= corr;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = u * AD_GROUPS + grp;
+          if (j < cnt) {
+            const float pj = __expf(sc[u] - mn);
+            l += pj;
+            float vf[8];
+            unpack8<__half>(*reinterpret_cast<const vec8*>(vs + j * D), vf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += pj * vf[i];
+          }
+        }
+        m = mn;
+      }
+      if (it + AD_STAGES < my_pages) {  // refill this stage once every thread has read it
+        __syncthreads();
+        if (threadIdx.x == 0) issue(it + AD_STAGES);
+      }
     }
+    // merge the eight half-warps
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = jb + u * PASS + sub;
-      float kf[8];
-      unpack8<__half>(kv[u], kf);
-      float d = 0.f;
+    for (int i = 0; i < 8; ++i) osm[grp][l16 * 8 + i] = acc[i];
+    if (l16 == 0) {
+      gm[grp] = m;
+      gl[grp] = l;
+    }
+    __syncthreads();
+    {
+      const int d = threadIdx.x;  // AD_THREADS == D
+      float M = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d += qf[i] * kf[i];
+      for (int g2 = 0; g2 < AD_GROUPS; ++g2) M = fmaxf(M, gm[g2]);
+      float o = 0.f, den = 0.f;
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-      d *= scale;
-      if (j < cnt) {
-        if (l16 == 0) sc[j] = d;
-        lmax = fmaxf(lmax, d);
+      for (int g2 = 0; g2 < AD_GROUPS; ++g2) {
+        const float w = (gm[g2] == -INFINITY) ? 0.f : __expf(gm[g2] - M);
+        o += w * osm[g2][d];
+        den += w * gl[g2];
+      }
+      my_part[d] = o;
+      if (d == 0) {
+        my_part[D] = M;
+        my_part[D + 1] = den;
       }
     }
   }
-  const float m = block_max(lmax, red);
-  // phase 2: exponentials
-  float lsum = 0.f;
-  for (int j = threadIdx.x; j < cnt; j += AD_THREADS) {
-    const float e = __expf(sc[j] - m);
-    sc[j] = e;
-    lsum += e;
-  }
-  const float l = block_sum(lsum, red);
-  // phase 3: O = sum_j p_j V[j].  16 lanes x 16 bytes cover one 256-byte value row, so a warp folds two tokens
-  // per iteration and the 4 warps stride over the chunk; partial rows are reduced through shared memory.
-  __shared__ float osm[AD_THREADS / 16][D + 4];
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 4
-  for (int j = warp * 2 + sub; j < cnt; j += (AD_THREADS / 32) * 2) {
-    const int page = pg[j / KV_PAGE];
-    float vf[8];
-    unpack8<__half>(ld_stream_rw16(vcache + (((size_t)page * H + h) * KV_PAGE + (j % KV_PAGE)) * D + l16 * 8), vf);
-    const float pj = sc[j];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += pj * vf[i];
-  }
-  {
-    float* orow = osm[warp * 2 + sub];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) orow[l16 * 8 + i] = acc[i];
+  // ---- the last CTA of this (b, h) combines the partial results of the min(S, npages) active splits
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int arrived = atomicAdd(&counters[b * H + h], 1);
+    last_flag = (arrived == S - 1);
+    if (last_flag) counters[b * H + h] = 0;  // ready for the next launch (stream order)
   }
   __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
   {
-    const int d = threadIdx.x;  // AD_THREADS == D
-    float o = 0.f;
-#pragma unroll
-    for (int r = 0; r < AD_THREADS / 16; ++r) o += osm[r][d];
-    out[d] = o;
+    const int d = threadIdx.x;
+    const int ns = min(S, npages);
+    const float* p = part + ((size_t)b * H + h) * S * (D + 2);
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < ns; ++s2) M = fmaxf(M, __ldcg(p + s2 * (D + 2) + D));
+    float num = 0.f, den = 0.f;
+#pragma unroll 4
+    for (int s2 = 0; s2 < ns; ++s2) {
+      const float w = __expf(__ldcg(p + s2 * (D + 2) + D) - M);
+      num += w * __ldcg(p + s2 * (D + 2) + d);
+      den += w * __ldcg(p + s2 * (D + 2) + D + 1);
+    }
+    out[((size_t)b * H + h) * D + d] = __float2half_rn(num / den);
   }
-  if (threadIdx.x == 0) {
-    out[D] = m;
-    out[D + 1] = l;
-  }
-}
-
-__global__ void __launch_bounds__(128) attn_decode_combine_kernel(const float* __restrict__ part,
-                                                                  __half* __restrict__ out, int H, int S) {
-  constexpr int D = 128;
-  pdl_trigger();
-  pdl_wait();
-  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
-  const float* p = part + ((size_t)b * H + h) * S * (D + 2);
-  float m = -INFINITY;
-  for (int s = 0; s < S; ++s) m = fmaxf(m, p[s * (D + 2) + D]);
-  float num = 0.f, den = 0.f;
-  for (int s = 0; s < S; ++s) {
-    const float ms = p[s * (D + 2) + D];
-    if (ms == -INFINITY) continue;
-    const float w = __expf(ms - m);
-    num += w * p[s * (D + 2) + d];
-    den += w * p[s * (D + 2) + D + 1];
-  }
-  out[((size_t)b * H + h) * D + d] = __float2half_rn(num / den);
 }
 
 SS_API int ss_attn_decode_paged_f16(const void* q, const void* kcache, const void* vcache, const int* seq_lens,
                                     const int* page_table, int max_pages, void* out, float* workspace, int B, int H,
                                     int D, int splits, float scale, void* stream) {
   SS_REQUIRE(D == 128, "decode attention is specialised for head_dim 128");
-  SS_REQUIRE(splits >= 1 && (max_pages + splits - 1) / splits * KV_PAGE <= AD_MAX_CHUNK,
-             "too few splits for max_pages (each split holds <= 1024 tokens)");
+  SS_REQUIRE(splits >= 1, "splits >= 1");
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  SS_CUDA(ss::launch_pdl(attn_decode_split_kernel, dim3(H, B, splits), dim3(AD_THREADS), 0, s, (const __half*)q,
-                         (const __half*)kcache, (const __half*)vcache, seq_lens, page_table, max_pages, workspace, H,
-                         splits, scale));
-  SS_CUDA(ss::launch_pdl(attn_decode_combine_kernel, dim3(H, B), dim3(128), 0, s, (const float*)workspace, (__half*)out,
-                         H, splits));
+  int* counters = reinterpret_cast<int*>(workspace + (size_t)B * H * splits * (D + 2));
+  static bool raised = false;
+  if (!raised) {
+    SS_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AD_SMEM));
+    raised = true;
+  }
+  SS_CUDA(ss::launch_pdl(attn_decode_kernel, dim3(H, B, splits), dim3(AD_THREADS), AD_SMEM, s, (const __half*)q,
+                         (const __half*)kcache, (const __half*)vcache, seq_lens, page_table, max_pages, workspace,
+                         counters, (__half*)out, H, splits, scale));
   SS_LAUNCH_CHECK();
   return 0;
 }

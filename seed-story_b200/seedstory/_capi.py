@@ -77,7 +77,7 @@ def check(rc):
 
 
 # kernels launched per C-ABI call (everything else launches exactly one); used for bench.py's `gpu_launches`
-_KERNELS_PER_CALL = {"ss_attn_decode_paged_f16": 2, "ss_groupnorm_nhwc": 2, "ss_fmha_path_counts": 0, "ss_groupnorm_ws_floats": 0, "ss_last_error": 0, "ss_version": 0,
+_KERNELS_PER_CALL = {"ss_groupnorm_nhwc": 2, "ss_fmha_path_counts": 0, "ss_gemm_row_stat_slots": 0, "ss_groupnorm_ws_floats": 0, "ss_last_error": 0, "ss_version": 0,
                      "ss_require_device": 0, "ss_stream_sync": 0}
 _launches = 0
 

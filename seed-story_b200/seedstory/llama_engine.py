@@ -43,13 +43,13 @@ def rope_tables_f16(head_dim, n_pos, device, base=10000.0):
 
 
 class LlamaEngine:
-    def __init__(self, cfg, device, max_batch=1, max_ctx=4096, max_new=512, decode_splits=32):
+    def __init__(self, cfg, device, max_batch=1, max_ctx=4096, max_new=512, decode_splits=12):
         ops.require_device()
         self.cfg, self.dev = cfg, device
         self.max_batch = max_batch
         self.max_pages = (max_ctx + PAGE - 1) // PAGE
         self.max_new = max_new
-        self.splits = max(decode_splits, (self.max_pages * PAGE + 1023) // 1024)
+        self.splits = max(1, decode_splits)
         c = cfg
         assert c.head_dim == 128, "attention kernels are specialised for head_dim 128"
         self.w = None
@@ -84,7 +84,7 @@ class LlamaEngine:
         self.d_attn = torch.zeros((B, c.hidden), **f16)
         self.d_act = torch.zeros((B, c.inter), **f16)
         self.d_logits = torch.zeros((B, c.vocab), **f16)
-        self.d_ws = torch.zeros(B * c.heads * self.splits * (c.head_dim + 2), dtype=torch.float32, device=device)
+        self.d_ws = ops.attn_decode_workspace(B, c.heads, c.head_dim, self.splits, device)
         self.img_ids = None
         self.img_ids_h = [-1, -2]   # no image-token processor until set_image_token_ids()
         self.suppress_ids = None
@@ -110,6 +110,7 @@ class LlamaEngine:
             g, u = merged(L, "gate_proj"), merged(L, "up_proj")
             packed.append(dict(
                 qkv=torch.cat([q, k, v], 0).contiguous(),
+                qkv_dec=ops.interleave_rope_rows(torch.cat([q, k, v], 0), self.cfg.heads, self.cfg.head_dim),
                 o=merged(L, "o_proj"),
                 gate_up=torch.stack([g, u], dim=1).reshape(2 * g.shape[0], g.shape[1]).contiguous(),
                 down=merged(L, "down_proj"),
@@ -244,18 +245,18 @@ class LlamaEngine:
     def _decode_body(self, B):
         c, w = self.cfg, self.w
         scale = 1.0 / math.sqrt(c.head_dim)
-        h, xn, qkv, q, attn, act = (t[:B] for t in (self.d_h, self.d_xn, self.d_qkv, self.d_q, self.d_attn, self.d_act))
+        h, xn, q, attn, act = (t[:B] for t in (self.d_h, self.d_xn, self.d_q, self.d_attn, self.d_act))
         ops.gather_rows(w["embed"], self.cur_ids[:B], h)
         for li, L in enumerate(w["layers"]):
-            ops.rmsnorm(h, L["ln1"], c.eps, out=xn)
-            ops.skinny_gemm(xn, L["qkv"], out=qkv)
-            ops.rope_kv_append(qkv, q, self.k_pages[li], self.v_pages[li], self.tok_seq[:B], self.tok_pos[:B],
-                               self.tok_slot[:B], self.page_table, self.cos, self.sin, c.heads, c.head_dim)
+            # 5 launches per layer: [RMSNorm + q/k/v + RoPE + cache append] [attention] [o_proj + residual]
+            # [RMSNorm + gate/up + SwiGLU] [down_proj + residual]
+            ops.decode_qkv_rope_append(h, L["ln1"], c.eps, L["qkv_dec"], q, self.k_pages[li], self.v_pages[li],
+                                       self.tok_seq[:B], self.tok_pos[:B], self.tok_slot[:B], self.page_table, self.cos,
+                                       self.sin, c.heads, c.head_dim)
             ops.attn_decode_paged(q, self.k_pages[li], self.v_pages[li], self.seq_lens[:B], self.page_table, attn,
                                   self.d_ws, c.heads, c.head_dim, self.splits, scale)
             ops.skinny_gemm(attn, L["o"], ops.EPI_RESIDUAL, residual=h, out=h)
-            ops.rmsnorm(h, L["ln2"], c.eps, out=xn)
-            ops.skinny_gemm(xn, L["gate_up"], ops.EPI_SWIGLU, out=act)
+            ops.skinny_gemm_rmsnorm(h, L["ln2"], c.eps, L["gate_up"], ops.EPI_SWIGLU, out=act)
             ops.skinny_gemm(act, L["down"], ops.EPI_RESIDUAL, residual=h, out=h)
         ops.rmsnorm(h, w["norm"], c.eps, out=xn)
         ops.store_rows_indexed(xn, self.hist[:B], self.n_out[:B])

@@ -116,6 +116,40 @@ def skinny_gemm(x, W, epilogue=EPI_NONE, residual=None, out=None):
     return out
 
 
+def skinny_gemm_rmsnorm(x, gamma, eps, W, epilogue=EPI_NONE, out=None):
+    """epilogue(RMSNorm(x; gamma, eps) @ W^T) for x [B<=8, K]: the normalisation runs in the kernel prologue."""
+    _req_cuda(x, W)
+    B, K = x.shape
+    N = W.shape[0]
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    out = torch.empty((B, n_out), dtype=x.dtype, device=x.device) if out is None else out
+    _capi.call("ss_skinny_gemm_rmsnorm_f16", _p(x), x.stride(0), _p(gamma), ctypes.c_float(eps), _p(W), _p(out),
+               out.stride(0), B, N, K, epilogue, _stream())
+    return out
+
+
+def interleave_rope_rows(wqkv, H, D):
+    """[q | k | v] projection rows -> the layout ss_decode_qkv_rope_append_f16 consumes: inside every q and k head row
+    2i holds dim i and row 2i+1 dim i + D/2 (v rows unchanged)."""
+    HD = H * D
+    K = wqkv.shape[1]
+    qk = wqkv[:2 * HD].view(2 * H, 2, D // 2, K).transpose(1, 2).reshape(2 * HD, K)
+    return torch.cat([qk, wqkv[2 * HD:]], 0).contiguous()
+
+
+def decode_qkv_rope_append(x, gamma, eps, wqkv_il, q_out, kcache, vcache, tok_seq, tok_pos, tok_slot, page_table, cos_t,
+                           sin_t, H, D):
+    B, K = x.shape
+    _capi.call("ss_decode_qkv_rope_append_f16", _p(x), x.stride(0), _p(gamma), ctypes.c_float(eps), _p(wqkv_il),
+               _p(q_out), _p(kcache), _p(vcache), _p(tok_seq), _p(tok_pos), _p(tok_slot), B, _p(page_table),
+               page_table.shape[1], _p(cos_t), _p(sin_t), H, D, K, _stream())
+
+
+def attn_decode_workspace(B, H, D, splits, device):
+    """Partial results [B, H, splits, D+2] fp32 + B*H int32 arrival counters (zeroed once; the kernel re-zeroes them)."""
+    return torch.zeros(B * H * splits * (D + 2) + B * H, dtype=torch.float32, device=device)
+
+
 def rope_kv_append(qkv, q_out, kcache, vcache, tok_seq, tok_pos, tok_slot, page_table, cos_t, sin_t, H, D):
     ntok = qkv.shape[0]
     _capi.call("ss_rope_kv_append_f16", _p(qkv), qkv.stride(0), _p(q_out), _p(kcache), _p(vcache), _p(tok_seq),
@@ -223,11 +257,39 @@ def is_const_weight(w):
     return t is not None and t.data_ptr() == w.data_ptr()
 
 
+class FoldedLN:
+    """A LayerNorm folded into the Linear that consumes it (ss_gemm_tn_ln): y = LN(x; gamma, beta, eps) W^T + b is
+    evaluated as rstd (x W'^T - mean colsum) + shift on the RAW rows x, with W' = gamma (.) W rounded to the
+    compute type, colsum[n] = sum_k W'[n,k] and shift[n] = sum_k beta[k] W[n,k] + b[n] in fp32 (load-time packing)."""
+
+    def __init__(self, w, gamma, beta, eps, bias=None):
+        wf = w.float()
+        self.w = (wf * gamma.float()[None, :]).to(w.dtype).contiguous()
+        self.colsum = self.w.float().sum(1).contiguous()
+        shift = wf @ beta.float()
+        if bias is not None:
+            shift = shift + bias.float()
+        self.shift = shift.contiguous()
+        self.eps = float(eps)
+
+
+def gemm_row_stat_slots(M, N):
+    """Slots of (sum, sum of squares) a GEMM with `stats_out=` writes per output row for an [M, N] output."""
+    return int(_capi.lib().ss_gemm_row_stat_slots(M, N))
+
+
+def row_stats_buffer(M, N, device):
+    slots = gemm_row_stat_slots(M, N)
+    return torch.zeros((slots, M, 2), dtype=torch.float32, device=device)
+
+
 def gemm(a, w, bias=None, bias2=None, rows_per_group=0, residual=None, act=ACT_NONE, glu=GLU_NONE, alpha=1.0,
-         out=None, force_bn=0, w_const=None):
+         out=None, force_bn=0, w_const=None, ln=None, ln_stats=None, stats_out=None):
     """out[M, N or N/2] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores.  w_const (SS_GEMM_B_CONST: `w` is a
     weight matrix nothing queued on the stream writes, so its first tiles may be fetched before the PDL wait)
-    defaults to "is `w` a registered load-time weight" (register_const); unregistered operands are activations."""
+    defaults to "is `w` a registered load-time weight" (register_const); unregistered operands are activations.
+    ln=FoldedLN + ln_stats=[slots, M, 2]: `a` holds raw rows whose LayerNorm is folded into this GEMM (w must be
+    ln.w); stats_out=[slots, M, 2]: leave the row statistics of this GEMM's output for a later folded LayerNorm."""
     _req_cuda(a, w)
     if w_const is None:
         w_const = is_const_weight(w)
@@ -239,14 +301,30 @@ def gemm(a, w, bias=None, bias2=None, rows_per_group=0, residual=None, act=ACT_N
     if out is None:
         out = torch.empty((M, n_out), dtype=a.dtype, device=a.device)
     assert out.stride(1) == 1
-    def launch():
-        _capi.call("ss_gemm_tn", _dt(a), _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
-                   _p(bias), _p(bias2), rows_per_group, _p(residual),
-                   residual.stride(0) if residual is not None else 0, act, glu, ctypes.c_float(alpha), force_bn,
-                   1 if w_const else 0, _stream())
+    if ln is not None or stats_out is not None:
+        assert bias2 is None and alpha == 1.0 and force_bn == 0
+        if ln is not None:
+            assert bias is None and ln_stats is not None and ln_stats.shape[1] == M and w.data_ptr() == ln.w.data_ptr()
+        if stats_out is not None:
+            assert tuple(stats_out.shape) == (gemm_row_stat_slots(M, N), M, 2) and stats_out.dtype == torch.float32
+
+        def launch():
+            _capi.call("ss_gemm_tn_ln", _dt(a), _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
+                       _p(bias), _p(residual), residual.stride(0) if residual is not None else 0, act, glu,
+                       1 if w_const else 0, _p(ln_stats) if ln is not None else None,
+                       ln_stats.shape[0] if ln is not None else 0, _p(ln.colsum) if ln is not None else None,
+                       _p(ln.shift) if ln is not None else None, ctypes.c_float(ln.eps if ln is not None else 0.0),
+                       _p(stats_out), _stream())
+    else:
+        def launch():
+            _capi.call("ss_gemm_tn", _dt(a), _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
+                       _p(bias), _p(bias2), rows_per_group, _p(residual),
+                       residual.stride(0) if residual is not None else 0, act, glu, ctypes.c_float(alpha), force_bn,
+                       1 if w_const else 0, _stream())
     _e = _prof_begin()
     launch()
-    name = f"gemm {M}x{N}x{K}" + (" glu" if glu else "") + (" +res" if residual is not None else "")
+    name = f"gemm {M}x{N}x{K}" + (" glu" if glu else "") + (" +res" if residual is not None else "") + \
+        (" ln" if ln is not None else "") + (" +stats" if stats_out is not None else "")
     _prof_end(_e, name, 2.0 * M * N * K)
     if RECORD is not None:
         RECORD.append((name, 2.0 * M * N * K, launch))

@@ -13,6 +13,7 @@ permutes.  Conv weights are packed [Cout, 9*Cin] tap-major; GEGLU projections ar
 per image.  One UNet forward (+ CFG/Euler update) is captured into a CUDA graph and replayed per step.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -82,9 +83,9 @@ class _Res:
 
 
 class _T2D:
-    def __init__(self, sd, pre, depth, heads, dev):
+    def __init__(self, sd, pre, depth, heads, dev, fold_ln=True):
         g = lambda k: sd[pre + k].detach().to(dev, F16).contiguous()
-        self.heads, self.depth = heads, depth
+        self.heads, self.depth, self.fold_ln = heads, depth, fold_ln
         self.norm = (g(".norm.weight"), g(".norm.bias"))
         self.proj_in = (g(".proj_in.weight"), g(".proj_in.bias"))
         self.proj_out = (g(".proj_out.weight"), g(".proj_out.bias"))
@@ -102,12 +103,23 @@ class _T2D:
                 ff1=(_interleave_rows(g(b + ".ff.net.0.proj.weight")), _interleave_rows(g(b + ".ff.net.0.proj.bias"))),
                 ff2=(g(b + ".ff.net.2.weight"), g(b + ".ff.net.2.bias")),
                 kv_ctx=None))
+            if fold_ln:
+                # norm1 -> to_q/k/v, norm2 -> attn2.to_q, norm3 -> GEGLU proj: the LayerNorms are folded into the GEMMs
+                # (ops.FoldedLN); the unfolded copies of those three weights are dropped
+                blk = self.blocks[-1]
+                blk["qkv_f"] = ops.FoldedLN(blk["qkv"], blk["n1"][0], blk["n1"][1], 1e-5)
+                blk["q2_f"] = ops.FoldedLN(blk["q2"], blk["n2"][0], blk["n2"][1], 1e-5)
+                blk["ff1_f"] = ops.FoldedLN(blk["ff1"][0], blk["n3"][0], blk["n3"][1], 1e-5, bias=blk["ff1"][1])
+                blk["qkv"] = blk["q2"] = blk["ff1"] = None
 
 
 class UNetEngine:
-    def __init__(self, sd, cfg, device):
+    def __init__(self, sd, cfg, device, fold_ln=None):
         ops.require_device()
         self.cfg, self.dev = cfg, device
+        # LayerNorm -> Linear pairs of the transformer blocks as ONE GEMM each (SS_UNET_LNFOLD=0: separate LN launches)
+        self.fold_ln = (os.environ.get("SS_UNET_LNFOLD", "1") != "0") if fold_ln is None else bool(fold_ln)
+        self._ln_stats = {}
         ch = cfg["block_out_channels"]
         self.ch, self.nb = ch, len(ch)
         self.groups = cfg["norm_num_groups"]
@@ -133,12 +145,12 @@ class UNetEngine:
             blk = dict(res=[], attn=[], down=None)
             for j in range(cfg["layers_per_block"]):
                 blk["res"].append(res(f"down_blocks.{i}.resnets.{j}"))
-                blk["attn"].append(_T2D(sd, f"down_blocks.{i}.attentions.{j}", tl[i], heads[i], device) if tl[i] else None)
+                blk["attn"].append(_T2D(sd, f"down_blocks.{i}.attentions.{j}", tl[i], heads[i], device, self.fold_ln) if tl[i] else None)
             if i < self.nb - 1:
                 blk["down"] = (_pack_conv3(g(f"down_blocks.{i}.downsamplers.0.conv.weight")),
                                g(f"down_blocks.{i}.downsamplers.0.conv.bias"))
             self.down.append(blk)
-        self.mid = (res("mid_block.resnets.0"), _T2D(sd, "mid_block.attentions.0", tl[-1], heads[-1], device),
+        self.mid = (res("mid_block.resnets.0"), _T2D(sd, "mid_block.attentions.0", tl[-1], heads[-1], device, self.fold_ln),
                     res("mid_block.resnets.1"))
         self.up = []
         for i in range(self.nb):
@@ -146,7 +158,7 @@ class UNetEngine:
             blk = dict(res=[], attn=[], up=None)
             for j in range(cfg["layers_per_block"] + 1):
                 blk["res"].append(res(f"up_blocks.{i}.resnets.{j}"))
-                blk["attn"].append(_T2D(sd, f"up_blocks.{i}.attentions.{j}", tl[ri], heads[ri], device) if tl[ri] else None)
+                blk["attn"].append(_T2D(sd, f"up_blocks.{i}.attentions.{j}", tl[ri], heads[ri], device, self.fold_ln) if tl[ri] else None)
             if i < self.nb - 1:
                 blk["up"] = (_pack_conv3(g(f"up_blocks.{i}.upsamplers.0.conv.weight")),
                              g(f"up_blocks.{i}.upsamplers.0.conv.bias"))
@@ -223,8 +235,33 @@ class UNetEngine:
         D = C // heads
         scale = 1.0 / math.sqrt(D)
         res = x.view(M, C)
-        h = ops.gemm(self._gn(x, t.norm, 1e-6, False).view(M, C), t.proj_in[0], bias=t.proj_in[1])
         T = self.ctx_len
+        if t.fold_ln:
+            # every LayerNorm input is a GEMM output: that GEMM's epilogue leaves the row statistics (stats_out) and the
+            # consuming GEMM applies the normalisation in ITS epilogue (ln=): 8 launches per block instead of 11
+            st = self._ln_stats.get((M, C))
+            if st is None:
+                assert self._graph is None
+                st = self._ln_stats[(M, C)] = ops.row_stats_buffer(M, C, self.dev)
+            h = ops.gemm(self._gn(x, t.norm, 1e-6, False).view(M, C), t.proj_in[0], bias=t.proj_in[1], stats_out=st)
+            for b in t.blocks:
+                qkv = ops.gemm(h, b["qkv_f"].w, ln=b["qkv_f"], ln_stats=st)
+                a = torch.empty((M, C), dtype=F16, device=self.dev)
+                ops.fmha(qkv, qkv[:, C:], qkv[:, 2 * C:], a, N, heads, L, L, D, (L * 3 * C, 3 * C, D), (L * 3 * C, 3 * C, D),
+                         (L * 3 * C, 3 * C, D), (L * C, C, D), scale)
+                ops.gemm(a, b["o1"][0], bias=b["o1"][1], residual=h, out=h, stats_out=st)
+                q = ops.gemm(h, b["q2_f"].w, ln=b["q2_f"], ln_stats=st)
+                kv = b["kv_ctx"]
+                ops.fmha(q, kv, kv[:, C:], a, N, heads, L, T, D, (L * C, C, D), (T * 2 * C, 2 * C, D), (T * 2 * C, 2 * C, D),
+                         (L * C, C, D), scale)
+                ops.gemm(a, b["o2"][0], bias=b["o2"][1], residual=h, out=h, stats_out=st)
+                f = ops.gemm(h, b["ff1_f"].w, glu=ops.GLU_GEGLU, ln=b["ff1_f"], ln_stats=st)
+                ops.gemm(f, b["ff2"][0], bias=b["ff2"][1], residual=h, out=h, stats_out=st)
+                self.launches += 8
+            out = ops.gemm(h, t.proj_out[0], bias=t.proj_out[1], residual=res)
+            self.launches += 2
+            return out.view(N, H, W, C)
+        h = ops.gemm(self._gn(x, t.norm, 1e-6, False).view(M, C), t.proj_in[0], bias=t.proj_in[1])
         for b in t.blocks:
             y = ops.layernorm(h, b["n1"][0], b["n1"][1], 1e-5)
             qkv = ops.gemm(y, b["qkv"])

@@ -190,7 +190,7 @@ def test_dropins_generate_and_get_image_embeds_match_oracle(cuda_dev):
                               max_new_tokens=90, num_img_gen_tokens=64,
                               logits_processor=[AutoImageTokenGenerationProcessor(tk, 64), ForcedScheduleProcessor(sched)],
                               device=cuda_dev)
-    assert out["has_img_output"] and out["img_gen_feat"].shape == (1, 64, cfg["agent_dim"])
+    assert out["has_img_output"] and out["img_gen_feat"].shape == (1, 256, cfg["agent_dim"])
     # ---- oracle restatement of the same call chain on the same (fp16-rounded) weights, fp32 math
     f32 = lambda sd_: {k: v.detach().float().cpu() for k, v in sd_.items()}
     vit_sd = f32(pipe.visual_encoder.state_dict())

@@ -118,9 +118,9 @@ def test_rope_append_and_decode_attention(cuda_dev):
     # decode attention: one query per sequence attends to everything cached
     q = torch.randn(B, H * D, device=cuda_dev).half()
     seq_lens = torch.tensor(lens, device=cuda_dev, dtype=torch.int32)
-    for splits in (2, 8):
+    for splits in (1, 2, 8, 12, 32):   # 1 / 2: several pages per CTA (stage refill); 32: empty splits
         out = torch.empty(B, H * D, device=cuda_dev, dtype=torch.float16)
-        ws = torch.empty(B * H * splits * (D + 2), device=cuda_dev, dtype=torch.float32)
+        ws = ops.attn_decode_workspace(B, H, D, splits, cuda_dev)
         ops.attn_decode_paged(q, kc, vc, seq_lens, perm, out, ws, H, D, splits, 1.0 / math.sqrt(D))
         for b, n in enumerate(lens):
             qq = q[b].view(H, 1, D).float()
@@ -129,6 +129,45 @@ def test_rope_append_and_decode_attention(cuda_dev):
             p = torch.softmax(qq @ kk.transpose(1, 2) / math.sqrt(D), -1)
             ref = (p @ vv).reshape(H * D)
             _close(out[b], ref, rtol=2e-3, atol=2e-3, what=f"decode attn b={b} splits={splits}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 4, 8])
+def test_fused_decode_layer_kernels_equal_the_unfused_chain(cuda_dev, B):
+    """RMSNorm folded into the q/k/v and gate/up projections, RoPE + cache append folded into the q/k/v epilogue:
+    bit-identical to rmsnorm -> skinny GEMM -> rope_kv_append (same rounding chain, same reduction order)."""
+    from seedstory import ops
+    torch.manual_seed(10 + B)
+    H, D, K, I = 32, 128, 4096, 11008
+    eps = 1e-5
+    x = (torch.randn(B, K, device=cuda_dev) * 1.7).half()
+    gamma = (1.0 + 0.1 * torch.randn(K, device=cuda_dev)).half()
+    xn = ops.rmsnorm(x, gamma, eps)
+    # gate/up + SwiGLU, and a plain projection
+    Wp = (torch.randn(2 * I, K, device=cuda_dev) * 0.02).half()
+    assert torch.equal(ops.skinny_gemm_rmsnorm(x, gamma, eps, Wp, ops.EPI_SWIGLU), ops.skinny_gemm(xn, Wp, ops.EPI_SWIGLU))
+    assert torch.equal(ops.skinny_gemm_rmsnorm(x, gamma, eps, Wp[:4100]), ops.skinny_gemm(xn, Wp[:4100]))
+    # q/k/v + RoPE + append
+    Wqkv = (torch.randn(3 * H * D, K, device=cuda_dev) * 0.02).half()
+    Wil = ops.interleave_rope_rows(Wqkv, H, D)
+    max_pages = 8
+    npages = B * max_pages
+    perm = torch.randperm(npages, device=cuda_dev).int().view(B, max_pages).contiguous()
+    cos_t, sin_t = _rope_tables(D, 4096, cuda_dev)
+    seq = torch.arange(B, device=cuda_dev, dtype=torch.int32)
+    pos = torch.tensor([17 + 101 * b for b in range(B)], device=cuda_dev, dtype=torch.int32)
+    slot = torch.tensor([(63 + 37 * b) % (max_pages * 64) for b in range(B)], device=cuda_dev, dtype=torch.int32)
+    kc1 = torch.zeros(npages, H, 64, D, device=cuda_dev, dtype=torch.float16)
+    vc1 = torch.zeros_like(kc1)
+    kc2, vc2 = torch.zeros_like(kc1), torch.zeros_like(kc1)
+    q1 = torch.empty(B, H * D, device=cuda_dev, dtype=torch.float16)
+    q2 = torch.zeros_like(q1)
+    qkv = ops.skinny_gemm(xn, Wqkv)
+    ops.rope_kv_append(qkv, q1, kc1, vc1, seq, pos, slot, perm, cos_t, sin_t, H, D)
+    ops.decode_qkv_rope_append(x, gamma, eps, Wil, q2, kc2, vc2, seq, pos, slot, perm, cos_t, sin_t, H, D)
+    assert torch.equal(q1, q2), "fused q (RoPE) differs"
+    assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2), "fused K/V append differs"
+    assert kc2.abs().sum() > 0
 
 
 def test_logits_processor_argmax(cuda_dev):
@@ -399,3 +438,39 @@ def test_cfg_euler_step(cuda_dev):
     _close(lat, ref, rtol=2e-3, atol=2e-2, what="euler")
     _close(nxt[1, :, :C], ref.float() / math.sqrt(sigma_next ** 2 + 1), rtol=2e-3, atol=2e-3, what="scaled input")
     assert nxt[:, :, C:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("M,C", [(2048, 1280), (8192, 640), (300, 320)])
+def test_gemm_with_folded_layernorm(cuda_dev, M, C):
+    """LayerNorm -> Linear as one GEMM: the producer GEMM leaves per-row (sum, sum of squares) partials, the consumer
+    applies mean / rstd / gamma / beta in its epilogue (ss_gemm_tn_ln).  Checked against layernorm -> gemm in fp32."""
+    from seedstory import ops
+    torch.manual_seed(M + C)
+    a = torch.randn(M, C, device=cuda_dev).half()
+    w0 = (torch.randn(C, C, device=cuda_dev) * 0.03).half()
+    b0 = (torch.randn(C, device=cuda_dev) * 0.1).half()
+    res = (torch.randn(M, C, device=cuda_dev) * 2 + 0.7).half()      # rows with a non-zero mean
+    st = ops.row_stats_buffer(M, C, cuda_dev)
+    x = ops.gemm(a, w0, bias=b0, residual=res, stats_out=st)            # the LN input, with its row statistics
+    x_plain = ops.gemm(a, w0, bias=b0, residual=res)
+    assert torch.equal(x, x_plain), "stats_out must not change the GEMM's output"
+    s = st.sum(0)
+    xf = x.float()
+    assert torch.allclose(s[:, 0], xf.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (xf * xf).sum(1), rtol=1e-4, atol=1e-2)
+    gamma = (1.0 + 0.2 * torch.randn(C, device=cuda_dev)).half()
+    beta = (0.1 * torch.randn(C, device=cuda_dev)).half()
+    for N, glu, with_bias in [(C, 0, False), (3 * C, 0, False), (8 * C, ops.GLU_GEGLU, True)]:
+        w = (torch.randn(N, C, device=cuda_dev) * 0.03).half()
+        bias = (torch.randn(N, device=cuda_dev) * 0.1).half() if with_bias else None
+        f = ops.FoldedLN(w, gamma, beta, 1e-5, bias=bias)
+        y = ops.gemm(x, f.w, glu=glu, ln=f, ln_stats=st)
+        ln = torch.nn.functional.layer_norm(xf, (C,), gamma.float(), beta.float(), 1e-5)
+        ref = ln @ w.float().t() + (bias.float() if bias is not None else 0.0)
+        if glu:
+            val, gate = ref[:, 0::2], ref[:, 1::2]                      # interleaved (value_j, gate_j) columns
+            ref = val * torch.nn.functional.gelu(gate)
+        # same bound as LN (rounded to fp16) -> GEMM: 2e-3 of the output scale
+        _close(y, ref, rtol=4e-3, atol=4e-3 * ref.abs().max().item(), what=f"folded LN gemm N={N} glu={glu}")
+        y2 = ops.gemm(ops.layernorm(x, gamma, beta, 1e-5), w, bias=bias, glu=glu)
+        _close(y, y2, rtol=4e-3, atol=4e-3 * ref.abs().max().item(), what=f"folded vs unfolded N={N} glu={glu}")

@@ -58,7 +58,7 @@ if which in ("all", "attn"):
     pt = torch.arange(32, device=dev, dtype=torch.int32).view(1, 32)
     q = rnd(B, Hh * D)
     out = torch.empty_like(q)
-    ws = torch.empty(B * Hh * 8 * (D + 2), device=dev, dtype=torch.float32)
+    ws = ops.attn_decode_workspace(B, Hh, D, 8, dev)
     sl = torch.tensor([1100], device=dev, dtype=torch.int32)
     for _ in range(2):
         ops.attn_decode_paged(q, kc, vc, sl, pt, out, ws, Hh, D, 8, 0.088)
