@@ -245,6 +245,8 @@ def run_ours(args):
                 try:
                     extra["gpu_eager_baseline"] = gpu_eager_baseline(dev, args)
                 except Exception as e:   # a baseline must never take the bench line down
+                    import traceback
+                    traceback.print_exc()
                     extra["gpu_eager_baseline"] = dict(error=repr(e)[:300])
             if not args.no_cpu_baseline:
                 extra["cpu_baseline"] = cpu_baseline(args)

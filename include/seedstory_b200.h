@@ -78,8 +78,8 @@ SS_EXPORT int ss_decode_qkv_rope_append_f16(const void* x, int ldx, const void* 
                                             int K, void* stream);
 /* xops.memory_efficient_attention(q,k,v, LowerTriangularFromBottomRightMask) for q_len == 1 (:289-295)
  * over the pages retained in page_table (window + attention-sink pages); split over pages and merged by the last
- * CTA to arrive (one launch).  workspace: B*H*splits*(D+2) floats followed by B*H int32 arrival counters that must be
- * zero before the first call (the kernel leaves them zero). */
+ * CTA to arrive (one launch).  workspace: 1024 int32 arrival counters (B*H <= 1024; zero before the first call, the
+ * kernel leaves them zero) followed by B*H*splits*(D+2) floats of partial results. */
 SS_EXPORT int ss_attn_decode_paged_f16(const void* q, const void* kcache, const void* vcache, const int* seq_lens,
                                        const int* page_table, int max_pages, void* out, float* workspace, int B, int H,
                                        int D, int splits, float scale, void* stream);
@@ -127,7 +127,7 @@ SS_EXPORT int ss_kv_scatter_tokens_16b(void* kpool_layer, void* vpool_layer, con
  * 2 silu) -> round -> +residual -> round.  glu: 1 = first*gelu(second) (diffusers GEGLU), 2 =
  * silu(first)*second (LlamaMLP, :191) over interleaved column pairs, output width N/2.
  * force_bn: 0 = auto, else 64/128/160/256 (N tile of the single-CTA kernel; 256 may take the CTA-pair kernel);
- * 1160 / 1256 force the CTA-pair kernel with a 160- / 256-wide pair tile (test hooks).
+ * 1256 forces the CTA-pair kernel (256-wide pair tile; test hook).
  * flags: SS_GEMM_B_CONST = B is a weight matrix that no work queued on `stream` writes (an nn.Linear weight): its
  * first tiles are then fetched while the preceding kernel is still draining.  Leave it clear when B is an
  * activation (e.g. the q k^T product of the VAE mid-block attention). */

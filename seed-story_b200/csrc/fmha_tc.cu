@@ -660,26 +660,23 @@ template <int D>
 int launch_ft(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FtParams& p, int B,
               cudaStream_t s) {
   using S = FtSmem<D>;
-  static bool attr = false;
-  if (!attr) {
-    SS_CUDA(cudaFuncSetAttribute(fmha_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr = true;
-  }
   dim3 grid((p.Lq + FT_BM - 1) / FT_BM, p.H, B);
   if constexpr (D == 64) {
-    static int pingpong = -1;
-    if (pingpong < 0) {
-      const char* e = getenv("SS_FMHA_PINGPONG");
-      pingpong = e ? atoi(e) : 1;
+    // head_dim 64 (UNet self-attention, resamplers): the ping-pong kernel (two softmax groups, P in TMEM)
+    static bool attr_pp = false;
+    if (!attr_pp) {
       SS_CUDA(cudaFuncSetAttribute(fmha_tc_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+      attr_pp = true;
     }
-    if (pingpong) {
-      SS_CUDA(ss::launch_pdl(fmha_tc_pp_kernel, grid, dim3(FT_THREADS), (size_t)S::TOTAL, s, tq, tk, tv, p));
-      SS_LAUNCH_CHECK();
-      return 0;
+    SS_CUDA(ss::launch_pdl(fmha_tc_pp_kernel, grid, dim3(FT_THREADS), (size_t)S::TOTAL, s, tq, tk, tv, p));
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      SS_CUDA(cudaFuncSetAttribute(fmha_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+      attr = true;
     }
+    SS_CUDA(ss::launch_pdl(fmha_tc_kernel<D>, grid, dim3(FT_THREADS), (size_t)S::TOTAL, s, tq, tk, tv, p));
   }
-  SS_CUDA(ss::launch_pdl(fmha_tc_kernel<D>, grid, dim3(FT_THREADS), (size_t)S::TOTAL, s, tq, tk, tv, p));
   SS_LAUNCH_CHECK();
   return 0;
 }
@@ -720,22 +717,8 @@ int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, 
   p.q_col_per_head = (int)q_sh; p.k_col_per_head = (int)k_sh; p.v_col_per_head = (int)v_sh;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
-  {
-    static int stages = -1;
-    if (stages < 0) {
-      const char* e = getenv("SS_FMHA_STAGES");
-      stages = e ? atoi(e) : 4;
-      if (stages < 2) stages = 2;
-    }
-    p.stages = stages;
-    static int poly = -1;
-    if (poly < 0) {
-      const char* e = getenv("SS_FMHA_POLY");
-      poly = e ? atoi(e) : 0;
-      if (poly > 4) poly = 4;
-    }
-    p.poly = poly;
-  }
+  p.stages = 4;  // K/V ring depth (head_dim 128 uses its own 2-stage layout)
+  p.poly = 0;    // exponentials on the MUFU unit (the polynomial split measured no faster, profiles/r1_fmha_experiments.md)
   if (D == 64) return launch_ft<64>(tq, tk, tv, p, B, stream);
   return launch_ft<128>(tq, tk, tv, p, B, stream);
 }

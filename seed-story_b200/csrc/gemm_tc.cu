@@ -795,6 +795,7 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
+  ss::unify_carveout(reinterpret_cast<const void*>(gemm_tc_pair_kernel<T, CONV, PBN>));
   SS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<T, CONV, PBN>, ta, tb, tcm, p, n_tiles_n,
                              (int)total_pair_tiles));
   return 0;
@@ -803,22 +804,9 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 template <bool CONV>
 int dispatch_pair(int dtype, int pbn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
                   const GemmParams& p, int n_tiles_n, long long pair_tiles, cudaStream_t s) {
-  if (dtype == SS_F16) {
-    if (pbn == 160) return launch_pair<__half, CONV, 160>(ta, tb, tcm, p, n_tiles_n, pair_tiles, s);
-    return launch_pair<__half, CONV, 256>(ta, tb, tcm, p, n_tiles_n, pair_tiles, s);
-  }
-  if (pbn == 160) return launch_pair<__nv_bfloat16, CONV, 160>(ta, tb, tcm, p, n_tiles_n, pair_tiles, s);
+  (void)pbn;  // one pair tile width (256); a 160-wide pair tile measured no faster than the single-CTA 160 tile
+  if (dtype == SS_F16) return launch_pair<__half, CONV, 256>(ta, tb, tcm, p, n_tiles_n, pair_tiles, s);
   return launch_pair<__nv_bfloat16, CONV, 256>(ta, tb, tcm, p, n_tiles_n, pair_tiles, s);
-}
-
-// 0 = never, 1 = when the shape suits (default), 2 = whenever legal
-int pair_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SS_GEMM_PAIR");
-    v = e ? atoi(e) : 1;
-  }
-  return v;
 }
 
 // Tile selection by a wave-quantisation cost model, in units of "accumulator columns of tensor-core time":
@@ -848,53 +836,30 @@ int pick_bn_persist(long long m_tiles, int N, int glu, int force_bn) {
   if (N <= 64 && !glu) return 64;
   int best = 256;
   long long best_cost = tile_cost(m_tiles, N, 256);
-  static int mode160 = -1;  // SS_GEMM_TILE160: 0 never, 1 cost model, 2 (default) cost model but not under a GLU, whose
-                            // register-stored tail measured slower than the 256-wide / CTA-pair kernels
-  if (mode160 < 0) {
-    const char* e = getenv("SS_GEMM_TILE160");
-    mode160 = e ? atoi(e) : 2;
-  }
   const int cands[2] = {160, 128};
   for (int c : cands) {
-    if (c == 160 && (mode160 == 0 || (mode160 == 2 && glu))) continue;
+    if (c == 160 && glu) continue;  // the 160 tile's register-stored tail measured slower under a GLU epilogue
     const long long k = tile_cost(m_tiles, N, c);
     if (k < best_cost) best = c, best_cost = k;
   }
   return best;
 }
 
-// CTA-pair tile width for this problem: 0 (use the single-CTA persistent kernel), 160 or 256.
-// SS_GEMM_PAIR: 0 never, 1 (default) by the cost model, 2 whenever legal (256).  SS_GEMM_PAIR160=1 lets the cost model
-// pick the 160-wide pair tile as well (off by default).
+// CTA-pair tile width for this problem: 0 (use the single-CTA persistent kernel) or 256.  force_bn 1256 forces the
+// pair kernel (test hook).
 int pick_pair(long long m_tiles, int N, int glu, int force_bn) {
-  if (force_bn == 1160 || force_bn == 1256) return (N >= 160 && !(force_bn == 1160 && glu)) ? force_bn - 1000 : 0;  // test hooks
-  const int mode = pair_mode();
-  if (mode == 0 || force_bn == 64 || force_bn == 128 || force_bn == 160) return 0;
+  (void)glu;
+  if (force_bn == 1256) return N >= 256 ? 256 : 0;
+  if (force_bn == 64 || force_bn == 128 || force_bn == 160) return 0;
   if (N < 256) return 0;
-  if (mode == 2) return 256;
-  static int allow160 = -1;
-  if (allow160 < 0) {
-    const char* e = getenv("SS_GEMM_PAIR160");
-    allow160 = e ? atoi(e) : 0;  // measured no faster than the single-CTA 160 tile on the UNet shapes
-  }
   const long long single = tile_cost(m_tiles, N, pick_bn_persist(m_tiles, N, glu, 0));
-  int best = 0;
-  long long best_cost = single;
   const int pad256 = (N + 255) / 256 * 256;
   const long long pair_tiles256 = ((m_tiles + 1) / 2) * (pad256 / 256);
   if (pad256 * 100 <= N * 108 && pair_tiles256 >= 60) {
     if (force_bn == 256) return 256;
-    const long long k = pair_cost(m_tiles, N, 256);
-    if (k <= best_cost) best = 256, best_cost = k;
+    if (pair_cost(m_tiles, N, 256) <= single) return 256;
   }
-  // the 160-wide pair: no GLU (its register-stored tail is slow under the GLU epilogue), N a multiple of 160, and at
-  // least half a wave of clusters
-  if (allow160 && force_bn == 0 && !glu && N % 160 == 0 && m_tiles >= 2 &&
-      ((m_tiles + 1) / 2) * (N / 160) >= sm_count() / 4) {
-    const long long k = pair_cost(m_tiles, N, 160);
-    if (k < best_cost) best = 160, best_cost = k;
-  }
-  return best;
+  return 0;
 }
 
 int get_out_tmap(CUtensorMap* out, const void* C, int dtype, long long M, int n_out, int ldc) {

@@ -61,12 +61,13 @@ struct SkinnyFuse {
 // (m = batch index, rows 8..15 zero), so a lane streams ONE 16-byte piece of one weight row per 32-wide k-block;
 // the 8 warps interleave over k-blocks, keep two register batches of loads in flight (software pipeline) and
 // reduce their 8x8 partial results through shared memory.
-template <int EPI, int SG_WARPS, bool NORM>
-__global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half* __restrict__ x, int ldx,
+template <int EPI, int SG_WARPS, int NV>   // NV: 0 = x is used as given; 2 / 4 = RMSNorm prologue for K <= 4096 / 8192
+__global__ void __launch_bounds__(SG_WARPS * 32, 3) skinny_gemm_kernel(const __half* __restrict__ x, int ldx,
                                                                     const __half* __restrict__ W,
                                                                     __half* __restrict__ y, int ldy, int B, int N,
                                                                     int K, const __half* __restrict__ res, int ldr,
                                                                     const SkinnyFuse fz) {
+  constexpr bool NORM = NV > 0;
   __shared__ float part[SG_WARPS_MAX][8][8];  // [warp][batch][row]
   __shared__ float red[32];
   extern __shared__ __align__(16) uint8_t sg_dyn[];
@@ -112,31 +113,83 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
   };
   load_batch(wa, 0);  // weights are constants: in flight before we wait for the producer of x
   pdl_wait();
+  // EPI_ROPE_APPEND: everything the epilogue needs besides the dot product (cache slot, page, rotary factors) is
+  // fetched now, so that the tail of the CTA is arithmetic + one store instead of a chain of dependent loads
+  __half rope_cs = __float2half_rn(0.f), rope_sn = rope_cs;
+  long long rope_dst = -1;  // element offset inside q_out (sec 0) / the K or V page pool (sec 1, 2); -1 = nothing to store
+  int rope_sec = 0, rope_odd = 0;
+  if (EPI == EPI_ROPE_APPEND && threadIdx.x < 64) {
+    const int n = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const int row = row0 + r;
+    if (n < B && row < N) {
+      const int HD = fz.H * fz.D, half_d = fz.D >> 1;
+      const int sec = row / HD, within = row - sec * HD;
+      const int h = within / fz.D, p = within - h * fz.D;
+      const int seq = fz.tok_seq[n], pos = fz.tok_pos[n], slot = fz.tok_slot[n];
+      rope_sec = sec;
+      rope_odd = p & 1;
+      if (sec == 0) {
+        const int d = (p >> 1) + (p & 1) * half_d;
+        rope_dst = (long long)n * HD + h * fz.D + d;
+        rope_cs = fz.cos_t[(size_t)pos * fz.D + d];
+        rope_sn = fz.sin_t[(size_t)pos * fz.D + d];
+      } else {
+        const int page = fz.page_table[(size_t)seq * fz.max_pages + slot / KV_PAGE];
+        const long long base = (((long long)page * fz.H + h) * KV_PAGE + (slot % KV_PAGE)) * fz.D;
+        if (sec == 1) {
+          const int d = (p >> 1) + (p & 1) * half_d;
+          rope_dst = base + d;
+          rope_cs = fz.cos_t[(size_t)pos * fz.D + d];
+          rope_sn = fz.sin_t[(size_t)pos * fz.D + d];
+        } else {
+          rope_dst = base + p;  // v rows keep their natural order
+        }
+      }
+    }
+  }
   if (NORM) {
     // RMSNorm of the <= 8 activation rows, recomputed per CTA (8 KB per row out of L2) while the first weight batch
-    // is in flight; arithmetic and reduction order are those of rmsnorm_f16_kernel (256 threads, pieces tid, tid+256..)
+    // is in flight: one pass, the row pieces stay in registers between the sum of squares and the scaling; arithmetic
+    // and reduction order are those of rmsnorm_f16_kernel (256 threads, pieces tid, tid + 256, ...)
     const int nvec = K >> 3;
+    vec8 gv[NV > 0 ? NV : 1], xv[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = threadIdx.x + i * (SG_WARPS * 32);
+      gv[i] = (vi < nvec) ? ld_cached16(fz.gamma + vi * 8) : vec8{0u, 0u, 0u, 0u};
+      xv[i] = (vi < nvec) ? ld_cached16(x + vi * 8) : vec8{0u, 0u, 0u, 0u};
+    }
     for (int b = 0; b < B; ++b) {
-      const __half* xr = x + (size_t)b * ldx;
+      vec8 xn[NV > 0 ? NV : 1];  // next row's pieces: their latency hides behind this row's reduction
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = threadIdx.x + i * (SG_WARPS * 32);
+        xn[i] = (b + 1 < B && vi < nvec) ? ld_cached16(x + (size_t)(b + 1) * ldx + vi * 8) : vec8{0u, 0u, 0u, 0u};
+      }
       float ss = 0.f;
-      for (int vi = threadIdx.x; vi < nvec; vi += SG_WARPS * 32) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
         float f[8];
-        unpack8<__half>(ld_cached16(xr + vi * 8), f);
+        unpack8<__half>(xv[i], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
       }
       ss = block_sum(ss, red);
       const float rstd = __frsqrt_rn(ss / (float)K + fz.eps);
-      for (int vi = threadIdx.x; vi < nvec; vi += SG_WARPS * 32) {
-        float f[8];
-        unpack8<__half>(ld_cached16(xr + vi * 8), f);
-        vec8 wv = ld_cached16(fz.gamma + vi * 8);
-        const __half* wh = reinterpret_cast<const __half*>(&wv);
-        vec8 o;
-        __half* oh = reinterpret_cast<__half*>(&o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) oh[j] = __hmul(wh[j], __float2half_rn(f[j] * rstd));
-        *reinterpret_cast<vec8*>(xs + (size_t)b * xs_ld + vi * 8) = o;
+      for (int i = 0; i < NV; ++i) {
+        const int vi = threadIdx.x + i * (SG_WARPS * 32);
+        if (vi < nvec) {
+          float f[8];
+          unpack8<__half>(xv[i], f);
+          const __half* wh = reinterpret_cast<const __half*>(&gv[i]);
+          vec8 o;
+          __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) oh[j] = __hmul(wh[j], __float2half_rn(f[j] * rstd));
+          *reinterpret_cast<vec8*>(xs + (size_t)b * xs_ld + vi * 8) = o;
+        }
+        xv[i] = xn[i];
       }
     }
     __syncthreads();
@@ -182,26 +235,17 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
       for (int w = 0; w < SG_WARPS; ++w) acc += part[w][n][r];
       const __half o = __float2half_rn(acc);
       const __half other = __ushort_as_half(__shfl_xor_sync(0xffffffffu, __half_as_ushort(o), 1));
-      const int row = row0 + r;
-      const int HD = fz.H * fz.D, half_d = fz.D >> 1;
-      if (n < B && row < N) {
-        const int sec = row / HD, within = row - sec * HD;
-        const int h = within / fz.D, p = within - h * fz.D;
-        const int seq = fz.tok_seq[n], pos = fz.tok_pos[n], slot = fz.tok_slot[n];
-        const int page = fz.page_table[(size_t)seq * fz.max_pages + slot / KV_PAGE];
-        const size_t dst = (((size_t)page * fz.H + h) * KV_PAGE + (slot % KV_PAGE)) * fz.D;
-        if (sec == 2) {
-          fz.vcache[dst + p] = o;  // v rows keep their natural order
+      if (rope_dst >= 0) {
+        if (rope_sec == 2) {
+          fz.vcache[rope_dst] = o;
         } else {
-          const int d = (p >> 1) + (p & 1) * half_d;
-          const __half cs = fz.cos_t[(size_t)pos * fz.D + d], sn = fz.sin_t[(size_t)pos * fz.D + d];
           // d < D/2: x_d cos_d + (-x_{d+D/2}) sin_d ;  d >= D/2: x_d cos_d + x_{d-D/2} sin_d
-          const __half v = (p & 1) ? hadd_t(__hmul(o, cs), __hmul(other, sn))
-                                   : hadd_t(__hmul(o, cs), __hmul(__hneg(other), sn));
-          if (sec == 0)
-            fz.q_out[(size_t)n * HD + h * fz.D + d] = v;
+          const __half v = rope_odd ? hadd_t(__hmul(o, rope_cs), __hmul(other, rope_sn))
+                                    : hadd_t(__hmul(o, rope_cs), __hmul(__hneg(other), rope_sn));
+          if (rope_sec == 0)
+            fz.q_out[rope_dst] = v;
           else
-            fz.kcache[dst + d] = v;
+            fz.kcache[rope_dst] = v;
         }
       }
     }
@@ -224,18 +268,9 @@ __global__ void __launch_bounds__(SG_WARPS * 32) skinny_gemm_kernel(const __half
 template <int EPI, bool NORM>
 static int skinny_launch(const __half* xp, int ldx, const __half* Wp, __half* yp, int ldy, int B, int N, int K,
                          const __half* rp, int ldr, const SkinnyFuse& fz, cudaStream_t s) {
-  static int warps = 0;
-  if (warps == 0) {
-    const char* e = getenv("SS_SKINNY_WARPS");
-    warps = (e && atoi(e) == 4 && !NORM) ? 4 : 8;   // the NORM prologue reproduces rmsnorm_f16_kernel's 256-thread reduction
-  }
   const int grid = ceil_div(N, SG_ROWS);
   const size_t smem = NORM ? (size_t)B * (K + SG_XS_PAD) * sizeof(__half) : 0;
-  if (warps == 4) {
-    auto k = skinny_gemm_kernel<EPI, 4, NORM>;
-    SS_CUDA(ss::launch_pdl(k, dim3(grid), dim3(128), smem, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr, fz));
-  } else {
-    auto k = skinny_gemm_kernel<EPI, 8, NORM>;
+  auto go = [&](auto k) -> int {
     if (smem > 48 * 1024) {
       static bool raised = false;
       if (!raised) {
@@ -244,9 +279,12 @@ static int skinny_launch(const __half* xp, int ldx, const __half* Wp, __half* yp
       }
     }
     SS_CUDA(ss::launch_pdl(k, dim3(grid), dim3(256), smem, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr, fz));
-  }
-  SS_LAUNCH_CHECK();
-  return 0;
+    SS_LAUNCH_CHECK();
+    return 0;
+  };
+  if (!NORM) return go(skinny_gemm_kernel<EPI, 8, 0>);
+  if (K <= 4096) return go(skinny_gemm_kernel<EPI, 8, NORM ? 2 : 0>);
+  return go(skinny_gemm_kernel<EPI, 8, NORM ? 4 : 0>);
 }
 
 SS_API int ss_skinny_gemm_f16(const void* x, int ldx, const void* W, void* y, int ldy, int B, int N, int K,
@@ -385,6 +423,7 @@ SS_API int ss_rope_kv_append_f16(const void* qkv, int ld_qkv, void* q_out, void*
 constexpr int AD_THREADS = 128;
 constexpr int AD_GROUPS = AD_THREADS / 16;  // half-warps
 constexpr int AD_STAGES = 2;
+constexpr int AD_COUNTER_WORDS = 1024;   // arrival counters (one per (sequence, head)) at the front of the workspace
 constexpr int AD_PAGE_BYTES = KV_PAGE * 128 * 2;                 // one head's K (or V) rows of a page: 16 KB, contiguous
 constexpr int AD_SMEM = AD_STAGES * 2 * AD_PAGE_BYTES + 128;     // K + V per stage, + alignment slack
 
@@ -545,7 +584,9 @@ SS_API int ss_attn_decode_paged_f16(const void* q, const void* kcache, const voi
   SS_REQUIRE(splits >= 1, "splits >= 1");
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  int* counters = reinterpret_cast<int*>(workspace + (size_t)B * H * splits * (D + 2));
+  SS_REQUIRE(B * H <= AD_COUNTER_WORDS, "B * H exceeds the arrival-counter block of the workspace");
+  int* counters = reinterpret_cast<int*>(workspace);  // first AD_COUNTER_WORDS words; partial results follow
+  workspace += AD_COUNTER_WORDS;
   static bool raised = false;
   if (!raised) {
     SS_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AD_SMEM));
@@ -652,6 +693,7 @@ SS_API int ss_logits_process_argmax_f16(void* logits, int ld, int V, const int* 
                                         void* stream) {
   SS_REQUIRE(n_img_ids <= 1024 && n_suppress <= 1024, "image-token / suppress list too long");
   if (B == 0) return 0;
+  ss::unify_carveout(reinterpret_cast<const void*>(logits_argmax_kernel));
   logits_argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((__half*)logits, ld, V, last_ids, img_ids, n_img_ids,
                                                              suppress_ids, suppress_ids ? n_suppress : 0, next_ids);
   SS_LAUNCH_CHECK();
@@ -673,6 +715,7 @@ SS_API int ss_gather_rows_16b(const void* table, const int* ids, void* out, int 
                               void* stream) {
   SS_REQUIRE(width % 8 == 0 && ld_out % 8 == 0, "row width must be a multiple of 8 elements");
   if (ntok == 0) return 0;
+  ss::unify_carveout(reinterpret_cast<const void*>(gather_rows_kernel));
   gather_rows_kernel<<<ntok, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)table, ids, (uint16_t*)out, ld_out,
                                                             width);
   SS_LAUNCH_CHECK();
@@ -709,6 +752,7 @@ SS_API int ss_decode_advance(const int* next_ids, int* cur_ids, int* tok_pos, in
                              const int* schedule, int sched_cap, void* stream) {
   if (B == 0) return 0;
   SS_REQUIRE(B <= 32, "at most 32 sequences per rank");
+  ss::unify_carveout(reinterpret_cast<const void*>(decode_advance_kernel));
   decode_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(next_ids, cur_ids, tok_pos, tok_slot, seq_lens, out_ids,
                                                             out_cap, n_out, done, eos_id, B, schedule, sched_cap);
   SS_LAUNCH_CHECK();
@@ -730,6 +774,7 @@ SS_API int ss_store_rows_indexed_16b(const void* src, int ld_src, void* dst, int
                                      void* stream) {
   SS_REQUIRE(width % 8 == 0 && ld_src % 8 == 0, "width % 8");
   if (B == 0) return 0;
+  ss::unify_carveout(reinterpret_cast<const void*>(store_rows_indexed_kernel));
   store_rows_indexed_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, ld_src, (uint16_t*)dst, cap, idx,
                                                                 width);
   SS_LAUNCH_CHECK();

@@ -146,8 +146,9 @@ def decode_qkv_rope_append(x, gamma, eps, wqkv_il, q_out, kcache, vcache, tok_se
 
 
 def attn_decode_workspace(B, H, D, splits, device):
-    """Partial results [B, H, splits, D+2] fp32 + B*H int32 arrival counters (zeroed once; the kernel re-zeroes them)."""
-    return torch.zeros(B * H * splits * (D + 2) + B * H, dtype=torch.float32, device=device)
+    """1024 int32 arrival counters (zeroed once; the kernel re-zeroes them) + partial results [B, H, splits, D+2] fp32."""
+    assert B * H <= 1024
+    return torch.zeros(1024 + B * H * splits * (D + 2), dtype=torch.float32, device=device)
 
 
 def rope_kv_append(qkv, q_out, kcache, vcache, tok_seq, tok_pos, tok_slot, page_table, cos_t, sin_t, H, D):
@@ -232,7 +233,7 @@ def register_const(t):
 def register_const_tree(obj, skip=("kv_ctx",), _depth=0):
     """Register every CUDA tensor reachable through dicts / lists / tuples / plain objects under `obj`, except under
     keys or attributes named in `skip` (per-image buffers that kernels write)."""
-    if _depth > 6:
+    if _depth > 12:
         return
     if isinstance(obj, torch.Tensor):
         register_const(obj)

@@ -12,10 +12,10 @@ offline, so this module fabricates every one of them in the upstream on-disk lay
   * pretrained/visual_tokenizer/qwen_vit_G.pt, pretrained/seed_story/george_sft/pytorch_model.bin (agent: peft key
     layout), pretrained/stable-diffusion-xl-base-1.0/{scheduler,vae,unet}, the adapted de-tokenizer .bin.
 
-Random weights never emit `<img>` by themselves, so the agent checkpoint is *crafted*: every token embedding carries a
-constant component in one hidden dimension and the lm_head row of `<img>` reads it, so the greedy choice outside an
-image run is always `<img>` (the reference's processor then forces the 64 queries and `</img>`).  This gives the turn
-loop of both scripts real image output to work with.
+Random weights never emit `<img>` by themselves, so the agent checkpoint is *crafted*: token embeddings carry a one-hot
+"successor" code in a few hidden dimensions that the lm_head rows read, so that greedy decoding emits twelve letters and
+then `<img>` (the reference's processor then forces the 64 queries and `</img>`), over and over until max_new_tokens.
+This gives the turn loop of both scripts real text and image output to work with.
 """
 import json
 import os
@@ -138,13 +138,24 @@ def build_project(root, n_stories=1, n_captions=27, seed=0):
         for k in sd:                                     # LoRA B is zero at init: give the adapters signal
             if "lora_B" in k:
                 sd[k] = torch.randn_like(sd[k]) * 0.02
-        # craft: constant component in hidden dim 0 of every embedding, read by the <img> row of lm_head
+        # craft a successor chain: hidden dims 0..n carry a one-hot "what comes next" code in every token embedding and
+        # the lm_head rows read it.  Every token is followed by the first of 12 letters, each letter by the next one and
+        # the last letter by <img> (the reference's processor then forces the 64 queries and </img>, after which the
+        # chain starts over until max_new_tokens).  The turn text is therefore non-empty, as in real use: gen_george.py
+        # slices len('[INST]') characters past </img> when it evicts an image (:236), which needs text there.
         emb_k = [k for k in sd if k.endswith("embed_tokens.weight")][0]
         head_k = [k for k in sd if k.endswith("lm_head.weight")][0]
         boi = n_text          # first added token
-        sd[emb_k][:, 0] = 8.0
-        sd[head_k][:, 0] = 0.0
-        sd[head_k][boi, 0] = 4.0
+        letters = [3 + ord(c) for c in "abcdefghijkl"]          # byte-fallback ids: <unk>, <s>, </s>, then <0x00>..
+        nl = len(letters)
+        sd[emb_k][:, :nl + 1] = 0.0
+        sd[head_k][:, :nl + 1] = 0.0
+        sd[emb_k][:, 0] = 8.0                                    # default successor: the first letter
+        sd[head_k][letters[0], 0] = 4.0
+        for j, t in enumerate(letters):
+            sd[emb_k][t, 0] = 0.0
+            sd[emb_k][t, j + 1] = 8.0                            # letter j -> letter j + 1 ... last letter -> <img>
+            sd[head_k][letters[j + 1] if j + 1 < nl else boi, j + 1] = 4.0
         os.makedirs("pretrained/seed_story/george_sft", exist_ok=True)
         torch.save({k: v.half() for k, v in sd.items()}, "pretrained/seed_story/george_sft/pytorch_model.bin")
 

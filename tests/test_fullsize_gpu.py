@@ -123,8 +123,10 @@ def test_unet_full_width_blocks_match_oracle(cuda_dev):
     eps = eng.forward()[..., :4].permute(0, 3, 1, 2)
     torch.cuda.synchronize()
     tc, mma = ops.fmha_path_counts()
-    # 3 T2D x 1 layer: self-attention on tcgen05 (4096 / 1024 tokens), cross-attention (64 keys) on the mma.sync tile
-    assert tc == 3 and mma == 3, (tc, mma)
+    # every transformer layer: self-attention on tcgen05 (4096 / 1024 tokens), cross-attention (64 keys) on the
+    # mma.sync tile (down 2 + mid 1 + up 2 x 2 Transformer2D blocks of depth 1 = 7 layers)
+    n_layers = sum(t.depth for t in eng._all_t2d())
+    assert n_layers == 7 and tc == n_layers and mma == n_layers, (tc, mma, n_layers)
     torch.set_num_threads(min(32, torch.get_num_threads() or 8))
     with torch.no_grad():
         ref = SO.unet_forward(sd16, cfg, x.float().repeat(2, 1, 1, 1), torch.tensor([ts[0], ts[0]]), ctx.float(),

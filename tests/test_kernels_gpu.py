@@ -232,14 +232,14 @@ def test_gemm_tn_shapes(cuda_dev, dt):
         w = (torch.randn(N, K, device=cuda_dev) / math.sqrt(K)).to(dt)
         ref = a.float() @ w.float().t()
         torch.cuda.synchronize()
-        for bn in (0, 64, 128, 160, 256, 1160, 1256):   # 1160 / 1256: CTA-pair kernel, 160- / 256-wide pair tile
+        for bn in (0, 64, 128, 160, 256, 1256):   # 1256: CTA-pair kernel (256-wide pair tile)
             # alternate the weight-prefetch-before-PDL-wait path (load-time weights) and the activation-operand path
             c = ops.gemm(a, w, force_bn=bn, w_const=(bn % 128 == 0))
             _close(c, ref, rtol=tol, atol=tol * ref.abs().max().item(), what=f"gemm {M}x{N}x{K} bn={bn} {dt}")
 
 
-@pytest.mark.parametrize("bn,M", [(0, 300), (160, 300), (160, 128 * 150 + 17), (256, 300), (1160, 300),
-                                  (1160, 128 * 150 + 17), (1256, 300), (1256, 128 * 150 + 17)])
+@pytest.mark.parametrize("bn,M", [(0, 300), (160, 300), (160, 128 * 150 + 17), (256, 300), (1256, 300),
+                                  (1256, 128 * 150 + 17)])
 def test_gemm_tn_epilogues(cuda_dev, bn, M):
     """Every epilogue, on the auto tile, the 160-wide tile with one tile per CTA (the two epilogue groups take
     alternate fills + the register-stored tail) and with several tiles per CTA (groups alternate tiles)."""
@@ -298,8 +298,8 @@ def test_conv3x3(cuda_dev, dt):
             _close(y.permute(0, 3, 1, 2), ref, rtol=tol, atol=tol * ref.abs().max().item(), what="conv bn=256")
             y = ops.conv3x3(x_nhwc, w_p, bias=bias, force_bn=160)
             _close(y.permute(0, 3, 1, 2), ref, rtol=tol, atol=tol * ref.abs().max().item(), what="conv bn=160")
-            y = ops.conv3x3(x_nhwc, w_p, bias=bias, force_bn=1160)
-            _close(y.permute(0, 3, 1, 2), ref, rtol=tol, atol=tol * ref.abs().max().item(), what="conv pair 160")
+            y = ops.conv3x3(x_nhwc, w_p, bias=bias, force_bn=1256)
+            _close(y.permute(0, 3, 1, 2), ref, rtol=tol, atol=tol * ref.abs().max().item(), what="conv pair")
         y = ops.conv3x3(x_nhwc, w_p, bias=bias, bias2=temb, residual=res)
         ref2 = (ref.to(dt).float() + temb.float()[:, :, None, None]).to(dt).float() + res.permute(0, 3, 1, 2).float()
         _close(y.permute(0, 3, 1, 2), ref2, rtol=tol, atol=tol * ref2.abs().max().item(), what="conv+temb+res")

@@ -49,7 +49,7 @@ for (M, N, K, glu, cnt) in gemms:
         bias = None
     out = torch.empty(M, n_out, device=dev).half()
     row = []
-    for bn in (0, 160, 256, 1160):
+    for bn in (0, 160, 256, 1256):
         us = graph_time(lambda: ops.gemm(a, w, bias=bias, residual=res, glu=glu, out=out, force_bn=bn))
         row.append(f"bn{bn}: {us:7.2f} us {2.0*M*N*K/us/1e6:6.0f} TF")
     print(f"gemm {M}x{N}x{K} glu={glu} x{cnt}: " + " | ".join(row), flush=True)
@@ -63,7 +63,7 @@ for (Ni, H, W, Cin, Cout, cnt) in convs:
     bias = torch.randn(Cout, device=dev).to(dt)
     out = torch.empty(Ni, H, W, Cout, device=dev).to(dt)
     row = []
-    for bn in (0, 160, 256, 1160):
+    for bn in (0, 160, 256, 1256):
         us = graph_time(lambda: ops.conv3x3(x, w, bias=bias, out=out, force_bn=bn))
         row.append(f"bn{bn}: {us:7.2f} us {2.0*Ni*H*W*Cout*9*Cin/us/1e6:6.0f} TF")
     print(f"conv {Ni}x{H}x{W} {Cin}->{Cout} x{cnt}: " + " | ".join(row), flush=True)
