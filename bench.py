@@ -488,7 +488,7 @@ def gpu_eager_baseline(dev, args):
             from src.models.qwen_visual import VisionTransformerWithAttnPool
             with torch.device(dev):
                 vit = VisionTransformerWithAttnPool(**story.FULL["vit"])
-            vsd = {k: v.detach().half() for k, v in vit.state_dict().items()}
+            vsd = {k: v.detach().half().to(dev) for k, v in vit.state_dict().items()}   # (sincos tables are built on the host)
             del vit
             z = torch.zeros(1, 3, 448, 448, device=dev).half()
             vc = story.FULL["vit"]

@@ -70,12 +70,19 @@ SS_EXPORT int ss_skinny_gemm_rmsnorm_f16(const void* x, int ldx, const void* gam
 /* The attention input side of one decode layer in one launch (LlamaDecoderLayer.forward :341 + LlamaAttention.forward
  * :228-244): RMSNorm -> q/k/v projection -> apply_rotary_pos_emb -> q to q_out [B, H*D], k (post-RoPE) and v appended
  * to the paged cache.  Wqkv_il [3*H*D, K] = rows [q | k | v] where inside every q and k head the rows are
- * pair-interleaved (row 2i = dim i, row 2i+1 = dim i + D/2: a rotary pair sits in neighbouring rows); v rows natural. */
+ * pair-interleaved (row 2i = dim i, row 2i+1 = dim i + D/2: a rotary pair sits in neighbouring rows); v rows natural.
+ * kv_base [B], rope_cos / rope_sin [B, D]: the step constants ss_decode_rope_meta prepared (cache destination and
+ * rotary factors of each sequence's new token), so the kernel's tail has no dependent index loads. */
 SS_EXPORT int ss_decode_qkv_rope_append_f16(const void* x, int ldx, const void* gamma, float eps, const void* Wqkv_il,
-                                            void* q_out, void* kcache, void* vcache, const int* tok_seq,
-                                            const int* tok_pos, const int* tok_slot, int B, const int* page_table,
-                                            int max_pages, const void* cos_table, const void* sin_table, int H, int D,
-                                            int K, void* stream);
+                                            void* q_out, void* kcache, void* vcache, const long long* kv_base,
+                                            const void* rope_cos, const void* rope_sin, int B, int H, int D, int K,
+                                            void* stream);
+/* Once per decode step (not per layer): kv_base[b] = element offset, inside one layer's page pool, of (page of
+ * tok_slot[b], head 0, slot % 64, dim 0) — prepare_inputs_for_generation's position / cache bookkeeping (:796-852) —
+ * and the cos / sin table rows of tok_pos[b] (:150-151). */
+SS_EXPORT int ss_decode_rope_meta(const int* tok_seq, const int* tok_pos, const int* tok_slot, int B,
+                                  const int* page_table, int max_pages, const void* cos_table, const void* sin_table,
+                                  int H, int D, long long* kv_base, void* rope_cos, void* rope_sin, void* stream);
 /* xops.memory_efficient_attention(q,k,v, LowerTriangularFromBottomRightMask) for q_len == 1 (:289-295)
  * over the pages retained in page_table (window + attention-sink pages); split over pages and merged by the last
  * CTA to arrive (one launch).  workspace: 1024 int32 arrival counters (B*H <= 1024; zero before the first call, the
@@ -137,16 +144,16 @@ SS_EXPORT int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int l
                          int act, int glu, float alpha, int force_bn, int flags, void* stream);
 /* The same GEMM with a LayerNorm folded around it (the LN -> Linear pairs of diffusers' BasicTransformerBlock that
  * src/models_ipa/adapter_modules.py:455-466 reaches: norm1 -> attn1.to_q/k/v, norm2 -> attn2.to_q, norm3 -> ff.net.0).
- * Consumer side (ln_stats != NULL): A holds the RAW rows x [M,K], B holds W' = gamma (.) W, and the epilogue evaluates
- *   LN(x) W^T + b = rstd (x W'^T - mean ln_colsum) + ln_shift,   ln_colsum[n] = sum_k W'[n,k] (fp32),
- *   ln_shift[n] = sum_k beta[k] W[n,k] + b[n] (fp32); `bias` must be NULL.  mean / rstd of row m are formed from
- *   ln_slots partial (sum, sum of squares) pairs ln_stats[slot][m][2] (fp32) left by the GEMM that wrote x.
+ * Consumer side (ln_stats != NULL): A holds the RAW rows x [M,K]; B holds the row-centred, gamma-scaled weights
+ *   W''[n,k] = gamma[k] W[n,k] - mean_k(gamma[k] W[n,k]), for which x W''^T = (x - mean(x)) (gamma (.) W)^T, so that
+ *   LN(x) W^T + b = rstd (x W''^T) + bias with bias[n] = sum_k beta[k] W[n,k] + b[n] (passed as `bias`).  rstd of row m
+ *   is formed from ln_slots partial (sum, sum of squares) pairs ln_stats[slot][m][2] (fp32) left by the GEMM that
+ *   wrote x.
  * Producer side (stats_out != NULL, non-GLU): this GEMM leaves those partials for ITS output rows (of the values as
  *   stored, after bias / activation / residual), ss_gemm_row_stat_slots(M, N) slots, layout [slot][M][2] fp32. */
 SS_EXPORT int ss_gemm_tn_ln(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N,
                             int K, const void* bias, const void* residual, int ldr, int act, int glu, int flags,
-                            const float* ln_stats, int ln_slots, const float* ln_colsum, const float* ln_shift,
-                            float ln_eps, float* stats_out, void* stream);
+                            const float* ln_stats, int ln_slots, float ln_eps, float* stats_out, void* stream);
 SS_EXPORT int ss_gemm_row_stat_slots(int M, int N);
 /* 3x3 / stride 1 / pad 1 convolution on NHWC activations as an implicit GEMM (diffusers ResnetBlock2D
  * conv1/conv2, Up/Downsample convs, VAE decoder convs — SURVEY.md Appendix C).  w is [Cout, 9*Cin] with

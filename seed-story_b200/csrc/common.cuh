@@ -6,10 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <cstdlib>
-#include <mutex>
 #include <string>
-#include <unordered_set>
 
 // ---------------------------------------------------------------------------------------------
 // Error convention of the C-ABI: every entry point returns 0 on success, non-zero on failure and
@@ -155,30 +152,9 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 namespace ss {
-// Every kernel of a captured step asks for the SAME L1 / shared-memory split (all shared): consecutive kernels whose
-// carve-outs differ cannot be resident on an SM together, which defeats the PDL overlap between them.
-// (SS_CARVEOUT=0 leaves the driver's per-kernel choice — A/B aid while this is being measured.)
-inline int carveout_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SS_CARVEOUT");
-    v = e ? atoi(e) : 1;
-  }
-  return v;
-}
-inline void unify_carveout(const void* kernel) {
-  static std::mutex mu;
-  static std::unordered_set<const void*> done;
-  if (!carveout_mode()) return;
-  std::lock_guard<std::mutex> g(mu);
-  if (done.insert(kernel).second)
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
-
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args... args) {
-  unify_carveout(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -293,7 +293,6 @@ __global__ void upsample2x_kernel(const vec8* __restrict__ x, vec8* __restrict__
 SS_API int ss_upsample2x_nhwc_16b(const void* x, void* y, int N, int H, int W, int C, void* stream) {
   SS_REQUIRE(C % 8 == 0, "C % 8");
   const long long total = (long long)N * 4 * H * W * (C / 8);
-  ss::unify_carveout(reinterpret_cast<const void*>(upsample2x_kernel));
   upsample2x_kernel<<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const vec8*)x, (vec8*)y, N, H, W, C / 8);
   SS_LAUNCH_CHECK();
   return 0;
@@ -314,7 +313,6 @@ SS_API int ss_concat_channels_16b(const void* a, const void* b, void* out, long 
                                   void* stream) {
   SS_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "C % 8");
   const long long total = rows * ((Ca + Cb) / 8);
-  ss::unify_carveout(reinterpret_cast<const void*>(concat_rows_kernel));
   concat_rows_kernel<<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const vec8*)a, (const vec8*)b, (vec8*)out,
                                                                              rows, Ca / 8, Cb / 8);
   SS_LAUNCH_CHECK();
@@ -343,7 +341,6 @@ __global__ void im2col_s2_kernel(const vec8* __restrict__ x, vec8* __restrict__ 
 SS_API int ss_im2col3x3_s2_nhwc_16b(const void* x, void* cols, int N, int H, int W, int C, void* stream) {
   SS_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "C % 8, even H/W");
   const long long total = (long long)N * (H / 2) * (W / 2) * 9 * (C / 8);
-  ss::unify_carveout(reinterpret_cast<const void*>(im2col_s2_kernel));
   im2col_s2_kernel<<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const vec8*)x, (vec8*)cols, N, H, W, C / 8);
   SS_LAUNCH_CHECK();
   return 0;
@@ -380,7 +377,6 @@ __global__ void cfg_euler_kernel(const __half* __restrict__ eps, int eps_ld, __h
 }
 SS_API int ss_cfg_euler_step_f16(const void* eps, int eps_ld, void* latents, void* next_in, int in_ld, int HW, int C,
                                  float guidance, float sigma, float sigma_next, void* stream) {
-  ss::unify_carveout(reinterpret_cast<const void*>(cfg_euler_kernel));
   cfg_euler_kernel<<<ew_grid((long long)HW * C), EW_THREADS, 0, (cudaStream_t)stream>>>(
       (const __half*)eps, eps_ld, (__half*)latents, (__half*)next_in, in_ld, HW, C, guidance, sigma, sigma_next);
   SS_LAUNCH_CHECK();

@@ -36,15 +36,14 @@ struct GemmParams {
   float alpha;
   int M, N, K;
   int b_const;  // B is a weight matrix nothing on the stream writes: its first tiles may be fetched before the PDL wait
-  // LayerNorm folded around the GEMM.  Consumer side: A holds the RAW rows x, B holds W' = gamma (.) W, and the
-  // epilogue turns acc = x W'^T into LN(x) W^T + b = rstd (acc - mean colsum) + shift with colsum[n] = sum_k W'[n,k],
-  // shift[n] = sum_k beta[k] W[n,k] + b[n]; mean / rstd of a row come from `ln_slots` partial (sum, sum of squares)
-  // pairs laid out [slot][M] that the GEMM which produced x left behind.  Producer side: stats_out receives those
-  // partials for this GEMM's (rounded) output rows, two slots per N tile.
+  // LayerNorm folded around the GEMM.  Consumer side: A holds the RAW rows x, B holds the ROW-CENTRED weights
+  // W'' = gamma (.) W - rowmean(gamma (.) W), for which x W''^T = (x - mean(x)) (gamma (.) W)^T exactly (the mean
+  // subtraction rides on the contraction), so the epilogue only multiplies by rstd and adds `bias` = beta W^T + b;
+  // rstd of a row comes from `ln_slots` partial (sum, sum of squares) pairs laid out [slot][M] that the GEMM which
+  // produced x left behind.  Producer side: stats_out receives those partials for this GEMM's (rounded) output rows,
+  // two slots per N tile.
   const float* ln_stats;
   int ln_slots;
-  const float* ln_colsum;
-  const float* ln_shift;
   float ln_eps;
   float* stats_out;
   // conv mode
@@ -89,22 +88,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
   if (f_begin < nfills) request(n0 + f_begin * acc_per_fill);
   // folded LayerNorm, consumer side: this row's mean / rstd from the partial sums its producer left (summed in slot
   // order: deterministic); fetched while the main loop still runs
-  float ln_a = 1.f, ln_b = 0.f;  // v -> ln_a * v + ln_b * colsum[col] + shift[col]
+  float out_scale = p.alpha;  // accumulator -> value scale: alpha, times this row's rstd under a folded LayerNorm
   if (p.ln_stats) {
     float s1 = 0.f, s2 = 0.f;
     if (row_ok) {
       const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + m;
-      for (int sl = 0; sl < p.ln_slots; ++sl) {
-        const float2 v2 = st[(size_t)sl * p.M];
-        s1 += v2.x;
-        s2 += v2.y;
+      // eight slot loads in flight at a time (one memory latency per batch instead of one per slot)
+      for (int s0 = 0; s0 < p.ln_slots; s0 += 8) {
+        float2 v2[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v2[u] = (s0 + u < p.ln_slots) ? __ldcg(st + (size_t)(s0 + u) * p.M) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          s1 += v2[u].x;
+          s2 += v2[u].y;
+        }
       }
     }
     const float inv_k = 1.f / (float)p.K;
     const float mean = s1 * inv_k;
     const float var = fmaxf(s2 * inv_k - mean * mean, 0.f);
-    ln_a = rsqrtf(var + p.ln_eps);
-    ln_b = -mean * ln_a;
+    out_scale *= rsqrtf(var + p.ln_eps);
   }
   float st_sum = 0.f, st_sq = 0.f;  // producer side: statistics of this thread's row over the columns it stores
   tc::mbar_wait(full_bar, full_parity);
@@ -153,24 +158,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       }
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * out_scale;
 #pragma unroll
       for (int gI = 0; gI < 4; ++gI) {
         float* vv = v + gI * 8;
         float bf[8];
-        if (p.ln_stats) {
-          const int col = min(col0 + gI * 8, p.N - 8);
-          const float4* cs = reinterpret_cast<const float4*>(p.ln_colsum + col);
-          const float4* sh = reinterpret_cast<const float4*>(p.ln_shift + col);
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const float4 c4 = __ldg(cs + hf), d4 = __ldg(sh + hf);
-            vv[hf * 4 + 0] = fmaf(ln_a, vv[hf * 4 + 0], fmaf(ln_b, c4.x, d4.x));
-            vv[hf * 4 + 1] = fmaf(ln_a, vv[hf * 4 + 1], fmaf(ln_b, c4.y, d4.y));
-            vv[hf * 4 + 2] = fmaf(ln_a, vv[hf * 4 + 2], fmaf(ln_b, c4.z, d4.z));
-            vv[hf * 4 + 3] = fmaf(ln_a, vv[hf * 4 + 3], fmaf(ln_b, c4.w, d4.w));
-          }
-        }
         unpack8<T>(vb[gI], bf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) vv[i] = ss_num<T>::to_f(ss_num<T>::from_f(vv[i] + bf[i]));
@@ -795,7 +787,6 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  ss::unify_carveout(reinterpret_cast<const void*>(gemm_tc_pair_kernel<T, CONV, PBN>));
   SS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<T, CONV, PBN>, ta, tb, tcm, p, n_tiles_n,
                              (int)total_pair_tiles));
   return 0;
@@ -885,14 +876,13 @@ SS_API int ss_gemm_row_stat_slots(int M, int N) {
 static int gemm_tn_impl(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                         const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr, int act,
                         int glu, float alpha, int force_bn, int flags, const float* ln_stats, int ln_slots,
-                        const float* ln_colsum, const float* ln_shift, float ln_eps, float* stats_out, void* stream) {
+                        float ln_eps, float* stats_out, void* stream) {
   SS_REQUIRE(dtype == SS_F16 || dtype == SS_BF16, "dtype must be f16 or bf16");
   SS_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
   SS_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "N, K, lda, ldb, ldc % 8");
   SS_REQUIRE(glu == 0 || (act == 0 && residual == nullptr), "GLU epilogue excludes act/residual");
   SS_REQUIRE(bias2 == nullptr || rows_per_group > 0, "bias2 needs rows_per_group");
-  SS_REQUIRE(ln_stats == nullptr || (ln_slots > 0 && ln_colsum && ln_shift && bias == nullptr && bias2 == nullptr),
-             "folded LayerNorm needs slots, colsum and shift, and carries the bias inside `shift`");
+  SS_REQUIRE(ln_stats == nullptr || (ln_slots > 0 && bias2 == nullptr), "folded LayerNorm needs its statistics slots");
   SS_REQUIRE(stats_out == nullptr || glu == 0, "row statistics are produced by non-GLU epilogues");
   const long long m_tiles = (M + BM - 1) / BM;
   const int bn = pick_bn_persist(m_tiles, N, glu, force_bn);
@@ -921,8 +911,6 @@ static int gemm_tn_impl(int dtype, const void* A, int lda, const void* B, int ld
   p.b_const = (flags & 1 /* SS_GEMM_B_CONST */) ? 1 : 0;
   p.ln_stats = ln_stats;
   p.ln_slots = ln_slots;
-  p.ln_colsum = ln_colsum;
-  p.ln_shift = ln_shift;
   p.ln_eps = ln_eps;
   p.stats_out = stats_out;
   CUtensorMap tcm;
@@ -950,17 +938,17 @@ SS_API int ss_gemm_tn(int dtype, const void* A, int lda, const void* B, int ldb,
                       const void* bias, const void* bias2, int rows_per_group, const void* residual, int ldr, int act,
                       int glu, float alpha, int force_bn, int flags, void* stream) {
   return gemm_tn_impl(dtype, A, lda, B, ldb, C, ldc, M, N, K, bias, bias2, rows_per_group, residual, ldr, act, glu, alpha,
-                      force_bn, flags, nullptr, 0, nullptr, nullptr, 0.f, nullptr, stream);
+                      force_bn, flags, nullptr, 0, 0.f, nullptr, stream);
 }
 
-// The same GEMM with a LayerNorm folded around it (include/seedstory_b200.h): `ln_*` apply LN to A's rows from row
-// statistics an earlier GEMM left in `ln_stats`; `stats_out` makes THIS GEMM leave the statistics of its output rows.
+// The same GEMM with a LayerNorm folded around it (include/seedstory_b200.h): `ln_stats` applies LN to A's rows from
+// the row statistics an earlier GEMM left (B must hold the row-centred gamma-scaled weights, `bias` = beta W^T + b);
+// `stats_out` makes THIS GEMM leave the statistics of its output rows.
 SS_API int ss_gemm_tn_ln(int dtype, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                          const void* bias, const void* residual, int ldr, int act, int glu, int flags,
-                         const float* ln_stats, int ln_slots, const float* ln_colsum, const float* ln_shift, float ln_eps,
-                         float* stats_out, void* stream) {
+                         const float* ln_stats, int ln_slots, float ln_eps, float* stats_out, void* stream) {
   return gemm_tn_impl(dtype, A, lda, B, ldb, C, ldc, M, N, K, bias, nullptr, 0, residual, ldr, act, glu, 1.f, 0, flags,
-                      ln_stats, ln_slots, ln_colsum, ln_shift, ln_eps, stats_out, stream);
+                      ln_stats, ln_slots, ln_eps, stats_out, stream);
 }
 
 // 3x3 stride-1 pad-1 convolution, NHWC activations [Nimg,H,W,Cin], weights [Cout, 9*Cin] with

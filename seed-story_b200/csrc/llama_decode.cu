@@ -11,7 +11,6 @@
 #include <cstdlib>
 
 #include "common.cuh"
-#include "tc.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // skinny GEMM
@@ -44,16 +43,12 @@ struct SkinnyFuse {
   float eps;
   // EPI_ROPE_APPEND: W rows of the q and k sections are stored pair-interleaved per head (row 2i = dim i, row 2i+1 =
   // dim i + D/2), so the two halves of a rotary pair are neighbours in the CTA's 8 output rows
-  __half* q_out;         // [B, H*D] natural order
-  __half* kcache;        // this layer's K pages [page][H][64][D]
+  __half* q_out;             // [B, H*D] natural order
+  __half* kcache;            // this layer's K pages [page][H][64][D]
   __half* vcache;
-  const int* tok_seq;
-  const int* tok_pos;
-  const int* tok_slot;
-  const int* page_table;
-  int max_pages;
-  const __half* cos_t;   // [max_pos, D] fp16
-  const __half* sin_t;
+  const long long* kv_base;  // [B] element offset of (page, head 0, slot % 64, dim 0) of each sequence's new token
+  const __half* rope_cs;     // [B, D] cos / sin rows of each sequence's position (ss_decode_rope_meta)
+  const __half* rope_sn;
   int H, D;
 };
 
@@ -125,25 +120,17 @@ __global__ void __launch_bounds__(SG_WARPS * 32, 3) skinny_gemm_kernel(const __h
       const int HD = fz.H * fz.D, half_d = fz.D >> 1;
       const int sec = row / HD, within = row - sec * HD;
       const int h = within / fz.D, p = within - h * fz.D;
-      const int seq = fz.tok_seq[n], pos = fz.tok_pos[n], slot = fz.tok_slot[n];
+      const int d = (p >> 1) + (p & 1) * half_d;   // q / k rows are pair-interleaved, v rows natural
       rope_sec = sec;
       rope_odd = p & 1;
       if (sec == 0) {
-        const int d = (p >> 1) + (p & 1) * half_d;
         rope_dst = (long long)n * HD + h * fz.D + d;
-        rope_cs = fz.cos_t[(size_t)pos * fz.D + d];
-        rope_sn = fz.sin_t[(size_t)pos * fz.D + d];
       } else {
-        const int page = fz.page_table[(size_t)seq * fz.max_pages + slot / KV_PAGE];
-        const long long base = (((long long)page * fz.H + h) * KV_PAGE + (slot % KV_PAGE)) * fz.D;
-        if (sec == 1) {
-          const int d = (p >> 1) + (p & 1) * half_d;
-          rope_dst = base + d;
-          rope_cs = fz.cos_t[(size_t)pos * fz.D + d];
-          rope_sn = fz.sin_t[(size_t)pos * fz.D + d];
-        } else {
-          rope_dst = base + p;  // v rows keep their natural order
-        }
+        rope_dst = fz.kv_base[n] + (long long)h * KV_PAGE * fz.D + (sec == 1 ? d : p);
+      }
+      if (sec != 2) {   // independent loads: no index chain in front of the rotary factors
+        rope_cs = fz.rope_cs[n * fz.D + d];
+        rope_sn = fz.rope_sn[n * fz.D + d];
       }
     }
   }
@@ -329,10 +316,9 @@ SS_API int ss_skinny_gemm_rmsnorm_f16(const void* x, int ldx, const void* gamma,
 // -> q to q_out, k (post-RoPE) and v appended to the paged cache (modeling_llama_xformer.py:341, 228-244).
 // Wqkv_il: [3*H*D, K]; inside every q and k head the rows are pair-interleaved (row 2i = dim i, 2i+1 = dim i + D/2).
 SS_API int ss_decode_qkv_rope_append_f16(const void* x, int ldx, const void* gamma, float eps, const void* Wqkv_il,
-                                         void* q_out, void* kcache, void* vcache, const int* tok_seq,
-                                         const int* tok_pos, const int* tok_slot, int B, const int* page_table,
-                                         int max_pages, const void* cos_table, const void* sin_table, int H, int D,
-                                         int K, void* stream) {
+                                         void* q_out, void* kcache, void* vcache, const long long* kv_base,
+                                         const void* rope_cos, const void* rope_sin, int B, int H, int D, int K,
+                                         void* stream) {
   SS_REQUIRE(B >= 1 && B <= 8, "decode handles 1..8 sequences");
   SS_REQUIRE(K % 32 == 0 && ldx % 8 == 0 && K <= 8192, "K must be a multiple of 32 (<= 8192), ldx of 8");
   SS_REQUIRE(D % 8 == 0 && D <= 256, "head dim must be a multiple of 8 and <= 256");
@@ -342,17 +328,44 @@ SS_API int ss_decode_qkv_rope_append_f16(const void* x, int ldx, const void* gam
   fz.q_out = (__half*)q_out;
   fz.kcache = (__half*)kcache;
   fz.vcache = (__half*)vcache;
-  fz.tok_seq = tok_seq;
-  fz.tok_pos = tok_pos;
-  fz.tok_slot = tok_slot;
-  fz.page_table = page_table;
-  fz.max_pages = max_pages;
-  fz.cos_t = (const __half*)cos_table;
-  fz.sin_t = (const __half*)sin_table;
+  fz.kv_base = kv_base;
+  fz.rope_cs = (const __half*)rope_cos;
+  fz.rope_sn = (const __half*)rope_sin;
   fz.H = H;
   fz.D = D;
   return skinny_launch<EPI_ROPE_APPEND, true>((const __half*)x, ldx, (const __half*)Wqkv_il, nullptr, 0, B, 3 * H * D, K,
                                               nullptr, 0, fz, (cudaStream_t)stream);
+}
+
+// Per-step constants of the fused q/k/v kernel, one CTA per sequence: where the new token's K / V rows go
+// (kv_base[b] = element offset of (page, head 0, slot % 64, dim 0); the page ids are the same in every layer) and the
+// cos / sin rows of its position.  Runs once per decode step (after the state advance), not once per layer.
+__global__ void decode_rope_meta_kernel(const int* __restrict__ tok_seq, const int* __restrict__ tok_pos,
+                                        const int* __restrict__ tok_slot, const int* __restrict__ page_table,
+                                        int max_pages, const __half* __restrict__ cos_t, const __half* __restrict__ sin_t,
+                                        int H, int D, long long* __restrict__ kv_base, __half* __restrict__ rope_cs,
+                                        __half* __restrict__ rope_sn) {
+  const int b = blockIdx.x;
+  const int seq = tok_seq[b], pos = tok_pos[b], slot = tok_slot[b];
+  if (threadIdx.x == 0) {
+    const int page = page_table[(size_t)seq * max_pages + slot / KV_PAGE];
+    kv_base[b] = ((long long)page * H * KV_PAGE + (slot % KV_PAGE)) * D;
+  }
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    rope_cs[(size_t)b * D + d] = cos_t[(size_t)pos * D + d];
+    rope_sn[(size_t)b * D + d] = sin_t[(size_t)pos * D + d];
+  }
+}
+
+SS_API int ss_decode_rope_meta(const int* tok_seq, const int* tok_pos, const int* tok_slot, int B, const int* page_table,
+                               int max_pages, const void* cos_table, const void* sin_table, int H, int D,
+                               long long* kv_base, void* rope_cos, void* rope_sin, void* stream) {
+  if (B == 0) return 0;
+  decode_rope_meta_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(tok_seq, tok_pos, tok_slot, page_table, max_pages,
+                                                                (const __half*)cos_table, (const __half*)sin_table, H, D,
+                                                                kv_base, (__half*)rope_cos, (__half*)rope_sin);
+  SS_LAUNCH_CHECK();
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -422,28 +435,21 @@ SS_API int ss_rope_kv_append_f16(const void* qkv, int ld_qkv, void* q_out, void*
 // ---------------------------------------------------------------------------------------------
 constexpr int AD_THREADS = 128;
 constexpr int AD_GROUPS = AD_THREADS / 16;  // half-warps
-constexpr int AD_STAGES = 2;
-constexpr int AD_COUNTER_WORDS = 1024;   // arrival counters (one per (sequence, head)) at the front of the workspace
-constexpr int AD_PAGE_BYTES = KV_PAGE * 128 * 2;                 // one head's K (or V) rows of a page: 16 KB, contiguous
-constexpr int AD_SMEM = AD_STAGES * 2 * AD_PAGE_BYTES + 128;     // K + V per stage, + alignment slack
+constexpr int AD_COUNTER_WORDS = 1024;      // arrival counters (one per (sequence, head)) at the front of the workspace
 
-__global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
+// NOTE on shared memory: this kernel deliberately uses only a few KB of STATIC shared memory.  A version that staged
+// the pages in 64 KB of dynamic shared memory (bulk copies) pushed the SMs' L1 / shared split to "all shared" for the
+// whole PDL-chained decode graph, and with the small L1 every weight-streaming GEMM of the step ran at ~60 % of its
+// bandwidth (decode step 3.1 -> 5.0 ms).  Pages are therefore staged in registers.
+__global__ void __launch_bounds__(AD_THREADS, 4) attn_decode_kernel(
     const __half* __restrict__ q, const __half* __restrict__ kcache, const __half* __restrict__ vcache,
     const int* __restrict__ seq_lens, const int* __restrict__ page_table, int max_pages, float* __restrict__ part,
     int* __restrict__ counters, __half* __restrict__ out, int H, int S, float scale) {
   constexpr int D = 128;
-  extern __shared__ uint8_t ad_dyn[];
   __shared__ float osm[AD_GROUPS][D + 4];
   __shared__ float gm[AD_GROUPS], gl[AD_GROUPS];
-  __shared__ __align__(8) uint64_t full_bar[AD_STAGES];
   __shared__ int last_flag;
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ad_dyn) + 127) & ~uintptr_t(127));
   pdl_trigger();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < AD_STAGES; ++i) tc::mbar_init(&full_bar[i], 1);
-    tc::fence_barrier_init();
-  }
-  __syncthreads();
   pdl_wait();  // q and the newest K/V row come from the preceding kernel
   const int h = blockIdx.x, b = blockIdx.y, s = blockIdx.z;
   const int n = seq_lens[b];
@@ -454,21 +460,6 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   float* my_part = part + (((size_t)b * H + h) * S + s) * (D + 2);
 
   if (s < npages) {
-    const int my_pages = (npages - s + S - 1) / S;  // pages s, s+S, ...
-    // page `it` of this CTA -> stage it % AD_STAGES: both the K and the V rows of the page arrive as two bulk copies
-    auto issue = [&](int it) {
-      const int pi = s + it * S;
-      const int page = page_table[(size_t)b * max_pages + pi];
-      const int cnt = min(KV_PAGE, n - pi * KV_PAGE);
-      const uint32_t bytes = (uint32_t)cnt * D * 2;
-      uint8_t* st = stage_base + (it % AD_STAGES) * 2 * AD_PAGE_BYTES;
-      uint64_t* bar = &full_bar[it % AD_STAGES];
-      tc::mbar_expect_tx(bar, 2 * bytes);
-      tc::bulk_load_1d(st, kcache + ((size_t)page * H + h) * KV_PAGE * D, bytes, bar);
-      tc::bulk_load_1d(st + AD_PAGE_BYTES, vcache + ((size_t)page * H + h) * KV_PAGE * D, bytes, bar);
-    };
-    if (threadIdx.x == 0)
-      for (int it = 0; it < min(AD_STAGES, my_pages); ++it) issue(it);
     float qf[8];
     unpack8<__half>(ld_cached16(q + ((size_t)b * H + h) * D + l16 * 8), qf);
 #pragma unroll
@@ -476,25 +467,37 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int it = 0; it < my_pages; ++it) {
-      const int pi = s + it * S;
+    for (int pi = s; pi < npages; pi += S) {
+      const int page = page_table[(size_t)b * max_pages + pi];
       const int cnt = min(KV_PAGE, n - pi * KV_PAGE);
-      const uint8_t* st = stage_base + (it % AD_STAGES) * 2 * AD_PAGE_BYTES;
-      tc::mbar_wait(&full_bar[it % AD_STAGES], (it / AD_STAGES) & 1);
-      const __half* ks = reinterpret_cast<const __half*>(st) + l16 * 8;
-      const __half* vs = reinterpret_cast<const __half*>(st + AD_PAGE_BYTES) + l16 * 8;
-      float sc[8], pm = -INFINITY;
+      const __half* kp = kcache + ((size_t)page * H + h) * KV_PAGE * D + l16 * 8;
+      const __half* vp = vcache + ((size_t)page * H + h) * KV_PAGE * D + l16 * 8;
+      // the whole page (this thread: 8 K and 8 V pieces of 16 bytes) is requested before anything is consumed
+      vec8 kv[8], vv[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int j = u * AD_GROUPS + grp;  // token of this half-warp in pass u
+        kv[u] = (j < cnt) ? ld_stream_rw16(kp + (size_t)j * D) : vec8{0u, 0u, 0u, 0u};
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = u * AD_GROUPS + grp;
+        vv[u] = (j < cnt) ? ld_stream_rw16(vp + (size_t)j * D) : vec8{0u, 0u, 0u, 0u};
+      }
+      asm volatile("" : "+r"(kv[0].x), "+r"(kv[1].x), "+r"(kv[2].x), "+r"(kv[3].x), "+r"(kv[4].x), "+r"(kv[5].x),
+                        "+r"(kv[6].x), "+r"(kv[7].x), "+r"(vv[0].x), "+r"(vv[1].x), "+r"(vv[2].x), "+r"(vv[3].x),
+                        "+r"(vv[4].x), "+r"(vv[5].x), "+r"(vv[6].x), "+r"(vv[7].x));
+      float sc[8], pm = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
         float kf[8];
-        unpack8<__half>(*reinterpret_cast<const vec8*>(ks + j * D), kf);
+        unpack8<__half>(kv[u], kf);
         float d = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) d += qf[i] * kf[i];
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        sc[u] = (j < cnt) ? d : -INFINITY;   // rows >= cnt of the stage hold stale bytes
+        sc[u] = (u * AD_GROUPS + grp < cnt) ? d : -INFINITY;
         pm = fmaxf(pm, sc[u]);
       }
       if (pm > -INFINITY) {  // (uniform per half-warp; the shuffles above ran converged)
@@ -505,21 +508,14 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
         for (int i = 0; i < 8; ++i) acc[i] *= corr;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int j = u * AD_GROUPS + grp;
-          if (j < cnt) {
-            const float pj = __expf(sc[u] - mn);
-            l += pj;
-            float vf[8];
-            unpack8<__half>(*reinterpret_cast<const vec8*>(vs + j * D), vf);
+          const float pj = __expf(sc[u] - mn);  // masked tokens: exp(-inf) = 0 (their V pieces are zeros)
+          l += pj;
+          float vf[8];
+          unpack8<__half>(vv[u], vf);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] += pj * vf[i];
-          }
+          for (int i = 0; i < 8; ++i) acc[i] += pj * vf[i];
         }
         m = mn;
-      }
-      if (it + AD_STAGES < my_pages) {  // refill this stage once every thread has read it
-        __syncthreads();
-        if (threadIdx.x == 0) issue(it + AD_STAGES);
       }
     }
     // merge the eight half-warps
@@ -587,12 +583,7 @@ SS_API int ss_attn_decode_paged_f16(const void* q, const void* kcache, const voi
   SS_REQUIRE(B * H <= AD_COUNTER_WORDS, "B * H exceeds the arrival-counter block of the workspace");
   int* counters = reinterpret_cast<int*>(workspace);  // first AD_COUNTER_WORDS words; partial results follow
   workspace += AD_COUNTER_WORDS;
-  static bool raised = false;
-  if (!raised) {
-    SS_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AD_SMEM));
-    raised = true;
-  }
-  SS_CUDA(ss::launch_pdl(attn_decode_kernel, dim3(H, B, splits), dim3(AD_THREADS), AD_SMEM, s, (const __half*)q,
+  SS_CUDA(ss::launch_pdl(attn_decode_kernel, dim3(H, B, splits), dim3(AD_THREADS), 0, s, (const __half*)q,
                          (const __half*)kcache, (const __half*)vcache, seq_lens, page_table, max_pages, workspace,
                          counters, (__half*)out, H, splits, scale));
   SS_LAUNCH_CHECK();
@@ -693,7 +684,6 @@ SS_API int ss_logits_process_argmax_f16(void* logits, int ld, int V, const int* 
                                         void* stream) {
   SS_REQUIRE(n_img_ids <= 1024 && n_suppress <= 1024, "image-token / suppress list too long");
   if (B == 0) return 0;
-  ss::unify_carveout(reinterpret_cast<const void*>(logits_argmax_kernel));
   logits_argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((__half*)logits, ld, V, last_ids, img_ids, n_img_ids,
                                                              suppress_ids, suppress_ids ? n_suppress : 0, next_ids);
   SS_LAUNCH_CHECK();
@@ -715,7 +705,6 @@ SS_API int ss_gather_rows_16b(const void* table, const int* ids, void* out, int 
                               void* stream) {
   SS_REQUIRE(width % 8 == 0 && ld_out % 8 == 0, "row width must be a multiple of 8 elements");
   if (ntok == 0) return 0;
-  ss::unify_carveout(reinterpret_cast<const void*>(gather_rows_kernel));
   gather_rows_kernel<<<ntok, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)table, ids, (uint16_t*)out, ld_out,
                                                             width);
   SS_LAUNCH_CHECK();
@@ -752,7 +741,6 @@ SS_API int ss_decode_advance(const int* next_ids, int* cur_ids, int* tok_pos, in
                              const int* schedule, int sched_cap, void* stream) {
   if (B == 0) return 0;
   SS_REQUIRE(B <= 32, "at most 32 sequences per rank");
-  ss::unify_carveout(reinterpret_cast<const void*>(decode_advance_kernel));
   decode_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(next_ids, cur_ids, tok_pos, tok_slot, seq_lens, out_ids,
                                                             out_cap, n_out, done, eos_id, B, schedule, sched_cap);
   SS_LAUNCH_CHECK();
@@ -774,7 +762,6 @@ SS_API int ss_store_rows_indexed_16b(const void* src, int ld_src, void* dst, int
                                      void* stream) {
   SS_REQUIRE(width % 8 == 0 && ld_src % 8 == 0, "width % 8");
   if (B == 0) return 0;
-  ss::unify_carveout(reinterpret_cast<const void*>(store_rows_indexed_kernel));
   store_rows_indexed_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, ld_src, (uint16_t*)dst, cap, idx,
                                                                 width);
   SS_LAUNCH_CHECK();

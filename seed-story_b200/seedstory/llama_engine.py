@@ -85,6 +85,10 @@ class LlamaEngine:
         self.d_act = torch.zeros((B, c.inter), **f16)
         self.d_logits = torch.zeros((B, c.vocab), **f16)
         self.d_ws = ops.attn_decode_workspace(B, c.heads, c.head_dim, self.splits, device)
+        # per-step constants of the fused q/k/v kernel (cache destination + rotary factors of each sequence's new token)
+        self.d_kv_base = torch.zeros(B, dtype=torch.int64, device=device)
+        self.d_rope_cs = torch.zeros((B, c.head_dim), **f16)
+        self.d_rope_sn = torch.zeros((B, c.head_dim), **f16)
         self.img_ids = None
         self.img_ids_h = [-1, -2]   # no image-token processor until set_image_token_ids()
         self.suppress_ids = None
@@ -251,8 +255,7 @@ class LlamaEngine:
             # 5 launches per layer: [RMSNorm + q/k/v + RoPE + cache append] [attention] [o_proj + residual]
             # [RMSNorm + gate/up + SwiGLU] [down_proj + residual]
             ops.decode_qkv_rope_append(h, L["ln1"], c.eps, L["qkv_dec"], q, self.k_pages[li], self.v_pages[li],
-                                       self.tok_seq[:B], self.tok_pos[:B], self.tok_slot[:B], self.page_table, self.cos,
-                                       self.sin, c.heads, c.head_dim)
+                                       self.d_kv_base[:B], self.d_rope_cs[:B], self.d_rope_sn[:B], c.heads, c.head_dim)
             ops.attn_decode_paged(q, self.k_pages[li], self.v_pages[li], self.seq_lens[:B], self.page_table, attn,
                                   self.d_ws, c.heads, c.head_dim, self.splits, scale)
             ops.skinny_gemm(attn, L["o"], ops.EPI_RESIDUAL, residual=h, out=h)
@@ -265,6 +268,12 @@ class LlamaEngine:
                                   self.suppress_ids)
         ops.decode_advance(self.next_ids[:B], self.cur_ids[:B], self.tok_pos[:B], self.tok_slot[:B], self.seq_lens[:B],
                            self.out_ids[:B], self.n_out[:B], self.done[:B], self.eos_id, self.schedule[:B])
+        self._rope_meta(B)      # for the NEXT step
+
+    def _rope_meta(self, B):
+        c = self.cfg
+        ops.decode_rope_meta(self.tok_seq[:B], self.tok_pos[:B], self.tok_slot[:B], self.page_table, self.cos, self.sin,
+                             c.heads, c.head_dim, self.d_kv_base[:B], self.d_rope_cs[:B], self.d_rope_sn[:B])
 
     def decode_step(self, B, use_graph=True):
         if not use_graph:
@@ -292,6 +301,7 @@ class LlamaEngine:
             for t, sv in zip((self.cur_ids, self.tok_pos, self.tok_slot, self.seq_lens, self.n_out, self.done,
                               self.out_ids), state):
                 t.copy_(sv)
+            self._rope_meta(B)     # the warm-up step advanced it
             self._graphs[B] = g
         g.replay()
         _capi.add_launches(self._graph_launches)
@@ -315,6 +325,7 @@ class LlamaEngine:
             self.schedule[:B].copy_(schedule)
         else:
             self.schedule[:B].fill_(-1)
+        self._rope_meta(B)
 
     def read_step(self, B):
         """4-byte-per-sequence read-back of the ids just emitted (the only host sync of a decode step)."""

@@ -137,12 +137,17 @@ def interleave_rope_rows(wqkv, H, D):
     return torch.cat([qk, wqkv[2 * HD:]], 0).contiguous()
 
 
-def decode_qkv_rope_append(x, gamma, eps, wqkv_il, q_out, kcache, vcache, tok_seq, tok_pos, tok_slot, page_table, cos_t,
-                           sin_t, H, D):
+def decode_rope_meta(tok_seq, tok_pos, tok_slot, page_table, cos_t, sin_t, H, D, kv_base, rope_cs, rope_sn):
+    """Step constants of decode_qkv_rope_append: kv_base [B] int64, rope_cs / rope_sn [B, D] fp16 (written)."""
+    B = tok_seq.numel()
+    _capi.call("ss_decode_rope_meta", _p(tok_seq), _p(tok_pos), _p(tok_slot), B, _p(page_table), page_table.shape[1],
+               _p(cos_t), _p(sin_t), H, D, _p(kv_base), _p(rope_cs), _p(rope_sn), _stream())
+
+
+def decode_qkv_rope_append(x, gamma, eps, wqkv_il, q_out, kcache, vcache, kv_base, rope_cs, rope_sn, H, D):
     B, K = x.shape
     _capi.call("ss_decode_qkv_rope_append_f16", _p(x), x.stride(0), _p(gamma), ctypes.c_float(eps), _p(wqkv_il),
-               _p(q_out), _p(kcache), _p(vcache), _p(tok_seq), _p(tok_pos), _p(tok_slot), B, _p(page_table),
-               page_table.shape[1], _p(cos_t), _p(sin_t), H, D, K, _stream())
+               _p(q_out), _p(kcache), _p(vcache), _p(kv_base), _p(rope_cs), _p(rope_sn), B, H, D, K, _stream())
 
 
 def attn_decode_workspace(B, H, D, splits, device):
@@ -260,17 +265,19 @@ def is_const_weight(w):
 
 class FoldedLN:
     """A LayerNorm folded into the Linear that consumes it (ss_gemm_tn_ln): y = LN(x; gamma, beta, eps) W^T + b is
-    evaluated as rstd (x W'^T - mean colsum) + shift on the RAW rows x, with W' = gamma (.) W rounded to the
-    compute type, colsum[n] = sum_k W'[n,k] and shift[n] = sum_k beta[k] W[n,k] + b[n] in fp32 (load-time packing)."""
+    evaluated as rstd (x W''^T) + shift on the RAW rows x, with the row-centred weights
+    W''[n,k] = gamma[k] W[n,k] - mean_k(gamma[k] W[n,k]) — x W''^T equals (x - mean(x)) (gamma (.) W)^T, the mean
+    subtraction rides on the contraction — and shift[n] = sum_k beta[k] W[n,k] + b[n] (load-time packing, fp32 math,
+    one rounding to the compute type)."""
 
     def __init__(self, w, gamma, beta, eps, bias=None):
         wf = w.float()
-        self.w = (wf * gamma.float()[None, :]).to(w.dtype).contiguous()
-        self.colsum = self.w.float().sum(1).contiguous()
+        wg = wf * gamma.float()[None, :]
+        self.w = (wg - wg.mean(dim=1, keepdim=True)).to(w.dtype).contiguous()
         shift = wf @ beta.float()
         if bias is not None:
             shift = shift + bias.float()
-        self.shift = shift.contiguous()
+        self.shift = shift.to(w.dtype).contiguous()
         self.eps = float(eps)
 
 
@@ -309,12 +316,13 @@ def gemm(a, w, bias=None, bias2=None, rows_per_group=0, residual=None, act=ACT_N
         if stats_out is not None:
             assert tuple(stats_out.shape) == (gemm_row_stat_slots(M, N), M, 2) and stats_out.dtype == torch.float32
 
+        ln_bias = ln.shift if ln is not None else bias
+
         def launch():
             _capi.call("ss_gemm_tn_ln", _dt(a), _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
-                       _p(bias), _p(residual), residual.stride(0) if residual is not None else 0, act, glu,
+                       _p(ln_bias), _p(residual), residual.stride(0) if residual is not None else 0, act, glu,
                        1 if w_const else 0, _p(ln_stats) if ln is not None else None,
-                       ln_stats.shape[0] if ln is not None else 0, _p(ln.colsum) if ln is not None else None,
-                       _p(ln.shift) if ln is not None else None, ctypes.c_float(ln.eps if ln is not None else 0.0),
+                       ln_stats.shape[0] if ln is not None else 0, ctypes.c_float(ln.eps if ln is not None else 0.0),
                        _p(stats_out), _stream())
     else:
         def launch():

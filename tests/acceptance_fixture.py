@@ -54,7 +54,14 @@ def build_tokenizer(path):
     for b in range(256):
         vocab[f"<0x{b:02X}>"] = len(vocab)
     vocab["▁"] = len(vocab)
-    tk = LlamaTokenizer(vocab=vocab, merges=[])
+    # whitespace runs (▁▁, ▁x4 … ▁x64) as the real Llama vocabulary has them: gen_george.py turns every image tag of a
+    # generated run into a space (:196), and 66 single-space tokens per run would blow the prompt past max positions
+    merges, piece = [], "▁"
+    for _ in range(6):
+        vocab[piece + piece] = len(vocab)
+        merges.append((piece, piece))
+        piece = piece + piece
+    tk = LlamaTokenizer(vocab=vocab, merges=merges)
     tk.add_tokens([BOI_TOKEN, EOI_TOKEN] + [IMG_TOKEN.format(i) for i in range(64)], special_tokens=True)
     os.makedirs(path, exist_ok=True)
     tk.save_pretrained(path)

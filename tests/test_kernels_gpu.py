@@ -164,7 +164,12 @@ def test_fused_decode_layer_kernels_equal_the_unfused_chain(cuda_dev, B):
     q2 = torch.zeros_like(q1)
     qkv = ops.skinny_gemm(xn, Wqkv)
     ops.rope_kv_append(qkv, q1, kc1, vc1, seq, pos, slot, perm, cos_t, sin_t, H, D)
-    ops.decode_qkv_rope_append(x, gamma, eps, Wil, q2, kc2, vc2, seq, pos, slot, perm, cos_t, sin_t, H, D)
+    kv_base = torch.zeros(B, dtype=torch.int64, device=cuda_dev)
+    rcs = torch.zeros(B, D, dtype=torch.float16, device=cuda_dev)
+    rsn = torch.zeros_like(rcs)
+    ops.decode_rope_meta(seq, pos, slot, perm, cos_t, sin_t, H, D, kv_base, rcs, rsn)
+    assert torch.equal(rcs, cos_t[pos.long()]) and torch.equal(rsn, sin_t[pos.long()])
+    ops.decode_qkv_rope_append(x, gamma, eps, Wil, q2, kc2, vc2, kv_base, rcs, rsn, H, D)
     assert torch.equal(q1, q2), "fused q (RoPE) differs"
     assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2), "fused K/V append differs"
     assert kc2.abs().sum() > 0

@@ -81,8 +81,12 @@ timed("rmsnorm + skinny qkv + rope_append (unfused)", lambda li: (ops.rmsnorm(x,
       ops.rope_kv_append(qkv, q, kc[li], vc[li], seq, pos, slot, pt, cos_t, sin_t, H, D)), qkv_bytes)
 timed("skinny qkv alone", lambda li: ops.skinny_gemm(xn, Wqkv[li], out=qkv), qkv_bytes)
 timed("rmsnorm alone", lambda li: ops.rmsnorm(x, gam, eps, out=xn), 1)
-timed("decode_qkv_rope_append (fused)", lambda li: ops.decode_qkv_rope_append(x, gam, eps, Wil[li], q, kc[li], vc[li], seq, pos, slot, pt,
-      cos_t, sin_t, H, D), qkv_bytes)
+kv_base = torch.zeros(B, dtype=torch.int64, device=dev)
+rcs = torch.zeros(B, D, dtype=torch.float16, device=dev)
+rsn = torch.zeros_like(rcs)
+ops.decode_rope_meta(seq, pos, slot, pt, cos_t, sin_t, H, D, kv_base, rcs, rsn)
+timed("decode_qkv_rope_append (fused)", lambda li: ops.decode_qkv_rope_append(x, gam, eps, Wil[li], q, kc[li], vc[li], kv_base, rcs, rsn,
+      H, D), qkv_bytes)
 timed("skinny_gemm_rmsnorm qkv (norm prologue only)", lambda li: ops.skinny_gemm_rmsnorm(x, gam, eps, Wqkv[li], out=qkv), qkv_bytes)
 gu_bytes = 2 * I * K * 2
 timed("rmsnorm + skinny gate_up swiglu (unfused)", lambda li: (ops.rmsnorm(x, gam, eps, out=xn),
@@ -92,6 +96,35 @@ timed("skinny_gemm_rmsnorm gate_up swiglu (fused)", lambda li: ops.skinny_gemm_r
 timed("skinny o_proj + residual", lambda li: ops.skinny_gemm(attn, Wo[li], ops.EPI_RESIDUAL, residual=hbuf, out=hbuf), K * K * 2)
 timed("skinny down_proj + residual", lambda li: ops.skinny_gemm(act, Wd[li], ops.EPI_RESIDUAL, residual=hbuf, out=hbuf), K * I * 2)
 kv_bytes = B * ctx * H * D * 2 * 2
+ws12 = ops.attn_decode_workspace(B, H, D, 12, dev)
+
+
+def layer_fused(li, with_attn=True):
+    ops.decode_qkv_rope_append(x, gam, eps, Wil[li], q, kc[li], vc[li], kv_base, rcs, rsn, H, D)
+    if with_attn:
+        ops.attn_decode_paged(q, kc[li], vc[li], lens, pt, attn, ws12, H, D, 12, scale)
+    ops.skinny_gemm(attn, Wo[li], ops.EPI_RESIDUAL, residual=hbuf, out=hbuf)
+    ops.skinny_gemm_rmsnorm(hbuf, gam, eps, Wgu[li], ops.EPI_SWIGLU, out=act)
+    ops.skinny_gemm(act, Wd[li], ops.EPI_RESIDUAL, residual=hbuf, out=hbuf)
+
+
+def layer_unfused(li, with_attn=True):
+    ops.rmsnorm(hbuf, gam, eps, out=xn)
+    ops.skinny_gemm(xn, Wqkv[li], out=qkv)
+    ops.rope_kv_append(qkv, q, kc[li], vc[li], seq, pos, slot, pt, cos_t, sin_t, H, D)
+    if with_attn:
+        ops.attn_decode_paged(q, kc[li], vc[li], lens, pt, attn, ws12, H, D, 12, scale)
+    ops.skinny_gemm(attn, Wo[li], ops.EPI_RESIDUAL, residual=hbuf, out=hbuf)
+    ops.rmsnorm(hbuf, gam, eps, out=xn)
+    ops.skinny_gemm(xn, Wgu[li], ops.EPI_SWIGLU, out=act)
+    ops.skinny_gemm(act, Wd[li], ops.EPI_RESIDUAL, residual=hbuf, out=hbuf)
+
+
+layer_bytes = qkv_bytes + gu_bytes + K * K * 2 + K * I * 2 + kv_bytes
+timed("whole layer, fused (5 launches)", layer_fused, layer_bytes)
+timed("whole layer, fused, no attention", lambda li: layer_fused(li, False), layer_bytes - kv_bytes)
+timed("whole layer, unfused (8 launches)", layer_unfused, layer_bytes)
+timed("whole layer, unfused, no attention", lambda li: layer_unfused(li, False), layer_bytes - kv_bytes)
 for splits in (6, 9, 12, 17, 24, 32):
     ws = ops.attn_decode_workspace(B, H, D, splits, dev)
     timed(f"attn_decode_paged splits={splits}", lambda li: ops.attn_decode_paged(q, kc[li], vc[li], lens, pt, attn, ws, H, D, splits, scale), kv_bytes)

@@ -70,5 +70,5 @@ lens = torch.tensor([1041, 77], device=dev, dtype=torch.int32)
 for splits in (1, 12, 32):
     ws = ops.attn_decode_workspace(B, H, D, splits, dev)
     out = torch.empty_like(q)
-    check(f"attn_decode_paged splits={splits}", lambda: ops.attn_decode_paged(q, kc, vc, lens, pt, out, ws, H, D, splits, 1 / math.sqrt(D)), reps=50)
+    check(f"attn_decode_paged splits={splits}", lambda: (ops.attn_decode_paged(q, kc, vc, lens, pt, out, ws, H, D, splits, 1 / math.sqrt(D)), out)[1], reps=50)
 print("done")

@@ -38,11 +38,23 @@ if which == "gemm2":
     for _ in range(2):
         ops.mha_packed(q, k, v, 20, 0.125)
 if which in ("all", "skinny"):
-    for (N, K) in [(12288, 4096), (4096, 4096), (22016, 4096), (4096, 11008), (32066, 4096)]:
+    for (N, K) in [(4096, 4096), (4096, 11008), (32066, 4096)]:
         Ws = [rnd(N, K, sc=0.02) for _ in range(3)]
         x = rnd(1, K)
+        res = rnd(1, N)
         for W_ in Ws:
-            ops.skinny_gemm(x, W_)
+            ops.skinny_gemm(x, W_, ops.EPI_RESIDUAL, residual=res)
+    # the fused decode-layer kernels: RMSNorm + q/k/v + RoPE + append, RMSNorm + gate/up + SwiGLU
+    Hh, D, K = 32, 128, 4096
+    x, gam = rnd(1, K), rnd(K)
+    kc, vc = rnd(40, Hh, 64, D), rnd(40, Hh, 64, D)
+    q = torch.empty(1, Hh * D, device=dev, dtype=torch.float16)
+    kvb = torch.zeros(1, dtype=torch.int64, device=dev)
+    rcs, rsn = rnd(1, D), rnd(1, D)
+    for _ in range(3):
+        ops.decode_qkv_rope_append(x, gam, 1e-5, rnd(3 * Hh * D, K, sc=0.02), q, kc, vc, kvb, rcs, rsn, Hh, D)
+    for _ in range(3):
+        ops.skinny_gemm_rmsnorm(x, gam, 1e-5, rnd(22016, K, sc=0.02), ops.EPI_SWIGLU)
 if which == "fmha1":
     q, k, v = rnd(2, 4096, 640), rnd(2, 4096, 640), rnd(2, 4096, 640)
     for _ in range(2):
@@ -58,10 +70,10 @@ if which in ("all", "attn"):
     pt = torch.arange(32, device=dev, dtype=torch.int32).view(1, 32)
     q = rnd(B, Hh * D)
     out = torch.empty_like(q)
-    ws = ops.attn_decode_workspace(B, Hh, D, 8, dev)
+    ws = ops.attn_decode_workspace(B, Hh, D, 12, dev)
     sl = torch.tensor([1100], device=dev, dtype=torch.int32)
     for _ in range(2):
-        ops.attn_decode_paged(q, kc, vc, sl, pt, out, ws, Hh, D, 8, 0.088)
+        ops.attn_decode_paged(q, kc, vc, sl, pt, out, ws, Hh, D, 12, 0.088)
     x = rnd(2, 64, 64, 640)
     g, b = rnd(640), rnd(640)
     wsn = ops.groupnorm_ws(2, 64 * 64, 640, 32, dev)
