@@ -143,9 +143,8 @@ __global__ void groupnorm_partial_kernel(const T* __restrict__ x, float* __restr
     out[0] = s;
     out[1] = q;
   }
-  // The CTA that finishes LAST for image n folds the per-CTA partials into (mean, rstd): one warp per group, lanes
-  // stride over the partials, fixed-order butterfly — the reduction order does not depend on which CTA does it, so
-  // results stay bit-reproducible.  (Replaces a separate finalize launch.)
+  // The CTA that finishes LAST for image n folds the per-CTA partials into (mean, rstd) in a fixed order — the result
+  // does not depend on which CTA does it, so it stays bit-reproducible.  (Replaces a separate finalize launch.)
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -155,23 +154,48 @@ __global__ void groupnorm_partial_kernel(const T* __restrict__ x, float* __restr
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // thread (slice, g): lanes of a warp read 32 consecutive groups of one chunk (256 contiguous bytes), 16 independent
+  // loads in flight per thread — a serial walk paid one L2 latency per chunk (~30 us of tail on ~600 chunks); the
+  // slice sums are then folded in slice order, so the result does not depend on which CTA runs this or on timing
   const int chunks = gridDim.x;
-  const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int g = warp; g < groups; g += nwarps) {
+  const int nslices = blockDim.x / 32;
+  float* red = gsm;  // [nslices][groups][2] (the pixel-lane buffer is dead by now)
+  {
+    const int sl = threadIdx.x / 32, gl = threadIdx.x % 32;
+    for (int g0 = 0; g0 < groups; g0 += 32) {
+      const int g = g0 + gl;
+      float s = 0.f, q = 0.f;
+      if (sl < nslices && g < groups) {
+        const float2* base = reinterpret_cast<const float2*>(partial) + (size_t)n * chunks * groups + g;
+        for (int c0 = sl; c0 < chunks; c0 += nslices * 16) {
+          float2 v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int c = c0 + u * nslices;
+            v[u] = c < chunks ? __ldcg(base + (size_t)c * groups) : make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            s += v[u].x;
+            q += v[u].y;
+          }
+        }
+        red[((size_t)sl * groups + g) * 2] = s;
+        red[((size_t)sl * groups + g) * 2 + 1] = q;
+      }
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float s = 0.f, q = 0.f;
-    for (int c = wl; c < chunks; c += 32) {
-      const float* p = partial + (((size_t)n * chunks + c) * groups + g) * 2;
-      s += __ldcg(p);
-      q += __ldcg(p + 1);
+    for (int sl = 0; sl < nslices; ++sl) {
+      s += red[((size_t)sl * groups + g) * 2];
+      q += red[((size_t)sl * groups + g) * 2 + 1];
     }
-    s = warp_sum(s);
-    q = warp_sum(q);
-    if (wl == 0) {
-      const float mean = s * inv_cnt;
-      const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
-      stats[2 * ((size_t)n * groups + g)] = mean;
-      stats[2 * ((size_t)n * groups + g) + 1] = rsqrtf(var + eps);
-    }
+    const float mean = s * inv_cnt;
+    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+    stats[2 * ((size_t)n * groups + g)] = mean;
+    stats[2 * ((size_t)n * groups + g) + 1] = rsqrtf(var + eps);
   }
   if (threadIdx.x == 0) tickets[n] = 0u;  // ready for the next call on this workspace
 }

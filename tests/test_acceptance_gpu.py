@@ -9,6 +9,7 @@ write `output/val_0/NN.jpg`.  Widths are reduced (tests/acceptance_fixture.py); 
 25-turn story length, the 8-image window, 50 Euler steps and (sink script) the KV slicing are the scripts' own."""
 import importlib.util
 import os
+import re
 import subprocess
 import sys
 
@@ -55,7 +56,7 @@ def _run_script(name, project):
 def test_gen_george_runs_unchanged(project):
     r = _run_script("gen_george.py", project)
     out = os.path.join(project[0], "output", "val_0")
-    imgs = sorted(f for f in os.listdir(out) if f[:2].isdigit() and f.endswith(".jpg"))
+    imgs = sorted(f for f in os.listdir(out) if re.fullmatch(r"\d\d\.jpg", f))
     # story_len 25: the loop runs until 24 images exist (gen_george.py:205-229) because every turn emits an image
     assert imgs[0] == "01.jpg" and len(imgs) == 24, imgs
     from PIL import Image
