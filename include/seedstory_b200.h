@@ -83,11 +83,6 @@ SS_EXPORT int ss_decode_qkv_rope_append_f16(const void* x, int ldx, const void* 
 SS_EXPORT int ss_decode_rope_meta(const int* tok_seq, const int* tok_pos, const int* tok_slot, int B,
                                   const int* page_table, int max_pages, const void* cos_table, const void* sin_table,
                                   int H, int D, long long* kv_base, void* rope_cos, void* rope_sin, void* stream);
-/* Hint for the NEXT decode-step kernel launched from this thread (ss_skinny_gemm*_f16, ss_decode_qkv_rope_append_f16,
- * ss_attn_decode_paged_f16): the bytes [ptr, ptr + bytes) are what the kernel AFTER it streams first (a weight
- * matrix); the launched kernel's last CTAs prefetch them into L2 so that HBM keeps working across the kernel
- * boundary.  One-shot (cleared by that launch); purely a performance hint — results never depend on it. */
-SS_EXPORT int ss_decode_prefetch_hint(const void* ptr, long long bytes);
 /* xops.memory_efficient_attention(q,k,v, LowerTriangularFromBottomRightMask) for q_len == 1 (:289-295)
  * over the pages retained in page_table (window + attention-sink pages); split over pages and merged by the last
  * CTA to arrive (one launch).  workspace: 1024 int32 arrival counters (B*H <= 1024; zero before the first call, the

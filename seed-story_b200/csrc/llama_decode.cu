@@ -30,36 +30,6 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// ---- L2 prefetch of the NEXT kernel's weights ----------------------------------------------------------------
-// A decode step is a chain of short weight-streaming kernels; every kernel boundary costs HBM idle time (the tail of
-// one kernel, the ramp-up of the next).  ss_decode_prefetch_hint() names the bytes the FOLLOWING kernel will stream
-// first; the last resident wave of CTAs of the kernel launched next issues cp.async.bulk.prefetch.L2 for them, so the
-// follower starts out of the 126 MB L2 while HBM keeps working through the boundary.
-constexpr int PF_CTAS = 296;  // CTAs (the last ones of the grid) that share the prefetch
-static thread_local const void* g_pf_ptr = nullptr;
-static thread_local long long g_pf_bytes = 0;
-
-__device__ __forceinline__ void l2_prefetch_slice(const void* p, long long bytes, int idx, int n) {
-  const long long per = ((bytes + n - 1) / n + 15) & ~15LL;
-  const long long off = per * idx;
-  if (off >= bytes) return;
-  long long len = (bytes - off < per ? bytes - off : per) & ~15LL;
-  const char* a = reinterpret_cast<const char*>(p) + off;
-  while (len > 0) {
-    const uint32_t c = len > 65536 ? 65536u : (uint32_t)len;
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(c) : "memory");
-    a += c;
-    len -= c;
-  }
-}
-
-SS_API int ss_decode_prefetch_hint(const void* ptr, long long bytes) {
-  SS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && bytes >= 0, "prefetch region must be 16-byte aligned");
-  g_pf_ptr = ptr;
-  g_pf_bytes = bytes & ~15LL;
-  return 0;
-}
-
 constexpr int SG_WARPS_MAX = 8;
 constexpr int SG_UNROLL = 8;   // k-blocks (32 wide) per register batch; two batches are in flight per warp
 constexpr int SG_ROWS = 8;     // weight rows per CTA
@@ -80,8 +50,6 @@ struct SkinnyFuse {
   const __half* rope_cs;     // [B, D] cos / sin rows of each sequence's position (ss_decode_rope_meta)
   const __half* rope_sn;
   int H, D;
-  const void* pf_ptr;    // next kernel's first bytes (ss_decode_prefetch_hint), or null
-  long long pf_bytes;
 };
 
 // One CTA = 8 rows of W.  The weight rows are the B operand (n = row), the <= 8 activation rows the A operand
@@ -219,10 +187,6 @@ __global__ void __launch_bounds__(SG_WARPS * 32, 3) skinny_gemm_kernel(const __h
     load_batch(wa, first + 2 * SG_UNROLL);
     compute_batch(wb, first + SG_UNROLL);
   }
-  if (fz.pf_ptr != nullptr && threadIdx.x == 0) {  // this CTA's own loads are all issued: help the next kernel
-    const int first = max(0, (int)gridDim.x - PF_CTAS);
-    if ((int)blockIdx.x >= first) l2_prefetch_slice(fz.pf_ptr, fz.pf_bytes, blockIdx.x - first, min((int)gridDim.x, PF_CTAS));
-  }
   // C fragment: c0,c1 -> (batch g, rows 2t,2t+1); c2,c3 belong to the zero half of A
   part[warp][g][2 * t] = c[0];
   part[warp][g][2 * t + 1] = c[1];
@@ -293,11 +257,6 @@ static int skinny_launch(const __half* xp, int ldx, const __half* Wp, __half* yp
                          const __half* rp, int ldr, const SkinnyFuse& fz, cudaStream_t s) {
   const int grid = ceil_div(N, SG_ROWS);
   const size_t smem = NORM ? (size_t)B * (K + SG_XS_PAD) * sizeof(__half) : 0;
-  SkinnyFuse fzp = fz;
-  fzp.pf_ptr = g_pf_ptr;
-  fzp.pf_bytes = g_pf_bytes;
-  g_pf_ptr = nullptr;
-  g_pf_bytes = 0;
   auto go = [&](auto k) -> int {
     if (smem > 48 * 1024) {
       static bool raised = false;
@@ -306,7 +265,7 @@ static int skinny_launch(const __half* xp, int ldx, const __half* Wp, __half* yp
         raised = true;
       }
     }
-    SS_CUDA(ss::launch_pdl(k, dim3(grid), dim3(256), smem, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr, fzp));
+    SS_CUDA(ss::launch_pdl(k, dim3(grid), dim3(256), smem, s, xp, ldx, Wp, yp, ldy, B, N, K, rp, ldr, fz));
     SS_LAUNCH_CHECK();
     return 0;
   };
@@ -485,8 +444,7 @@ constexpr int AD_COUNTER_WORDS = 1024;      // arrival counters (one per (sequen
 __global__ void __launch_bounds__(AD_THREADS, 4) attn_decode_kernel(
     const __half* __restrict__ q, const __half* __restrict__ kcache, const __half* __restrict__ vcache,
     const int* __restrict__ seq_lens, const int* __restrict__ page_table, int max_pages, float* __restrict__ part,
-    int* __restrict__ counters, __half* __restrict__ out, int H, int S, float scale, const void* pf_ptr,
-    long long pf_bytes) {
+    int* __restrict__ counters, __half* __restrict__ out, int H, int S, float scale) {
   constexpr int D = 128;
   __shared__ float osm[AD_GROUPS][D + 4];
   __shared__ float gm[AD_GROUPS], gl[AD_GROUPS];
@@ -587,10 +545,6 @@ __global__ void __launch_bounds__(AD_THREADS, 4) attn_decode_kernel(
       }
     }
   }
-  if (pf_ptr != nullptr && threadIdx.x == 0) {  // this kernel moves little data: every CTA prefetches a slice
-    const int nct = gridDim.x * gridDim.y * gridDim.z;
-    l2_prefetch_slice(pf_ptr, pf_bytes, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, nct);
-  }
   // ---- the last CTA of this (b, h) combines the partial results of the min(S, npages) active splits
   __threadfence();
   __syncthreads();
@@ -631,9 +585,7 @@ SS_API int ss_attn_decode_paged_f16(const void* q, const void* kcache, const voi
   workspace += AD_COUNTER_WORDS;
   SS_CUDA(ss::launch_pdl(attn_decode_kernel, dim3(H, B, splits), dim3(AD_THREADS), 0, s, (const __half*)q,
                          (const __half*)kcache, (const __half*)vcache, seq_lens, page_table, max_pages, workspace,
-                         counters, (__half*)out, H, splits, scale, g_pf_ptr, g_pf_bytes));
-  g_pf_ptr = nullptr;
-  g_pf_bytes = 0;
+                         counters, (__half*)out, H, splits, scale));
   SS_LAUNCH_CHECK();
   return 0;
 }

@@ -17,7 +17,6 @@ Data layout in HBM
             decode step is a single CUDA-graph replay with no host round trip except the 4-byte id read.
 """
 import math
-import os
 
 import torch
 
@@ -51,7 +50,6 @@ class LlamaEngine:
         self.max_pages = (max_ctx + PAGE - 1) // PAGE
         self.max_new = max_new
         self.splits = max(1, decode_splits)
-        self.l2_prefetch = os.environ.get("SS_DECODE_L2_PREFETCH", "1") != "0"   # A/B aid (see ss_decode_prefetch_hint)
         c = cfg
         assert c.head_dim == 128, "attention kernels are specialised for head_dim 128"
         self.w = None
@@ -256,19 +254,12 @@ class LlamaEngine:
         for li, L in enumerate(w["layers"]):
             # 5 launches per layer: [RMSNorm + q/k/v + RoPE + cache append] [attention] [o_proj + residual]
             # [RMSNorm + gate/up + SwiGLU] [down_proj + residual]
-            nxt = w["layers"][li + 1]["qkv_dec"] if li + 1 < len(w["layers"]) else w["lm_head"]
-            pf = ops.decode_prefetch_hint if self.l2_prefetch else (lambda *a, **k: None)
-            pf(L["o"])                                    # q/k/v kernel's tail -> o_proj weights
             ops.decode_qkv_rope_append(h, L["ln1"], c.eps, L["qkv_dec"], q, self.k_pages[li], self.v_pages[li],
                                        self.d_kv_base[:B], self.d_rope_cs[:B], self.d_rope_sn[:B], c.heads, c.head_dim)
-            pf(L["gate_up"])                              # attention (little traffic of its own) -> gate/up, first part
             ops.attn_decode_paged(q, self.k_pages[li], self.v_pages[li], self.seq_lens[:B], self.page_table, attn,
                                   self.d_ws, c.heads, c.head_dim, self.splits, scale)
-            pf(L["gate_up"], 48 << 20, 32 << 20)          # o_proj's tail -> gate/up, next part
             ops.skinny_gemm(attn, L["o"], ops.EPI_RESIDUAL, residual=h, out=h)
-            pf(L["down"])
             ops.skinny_gemm_rmsnorm(h, L["ln2"], c.eps, L["gate_up"], ops.EPI_SWIGLU, out=act)
-            pf(nxt)
             ops.skinny_gemm(act, L["down"], ops.EPI_RESIDUAL, residual=h, out=h)
         ops.rmsnorm(h, w["norm"], c.eps, out=xn)
         ops.store_rows_indexed(xn, self.hist[:B], self.n_out[:B])

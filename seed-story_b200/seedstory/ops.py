@@ -137,14 +137,6 @@ def interleave_rope_rows(wqkv, H, D):
     return torch.cat([qk, wqkv[2 * HD:]], 0).contiguous()
 
 
-def decode_prefetch_hint(t, offset_bytes=0, max_bytes=48 << 20):
-    """The next decode kernel launched prefetches t's bytes [offset, offset + max_bytes) into L2 (see the header)."""
-    total = t.numel() * t.element_size()
-    n = max(0, min(max_bytes, total - offset_bytes))
-    if n > 0:
-        _capi.lib().ss_decode_prefetch_hint(ctypes.c_void_p(t.data_ptr() + offset_bytes), ctypes.c_longlong(n))
-
-
 def decode_rope_meta(tok_seq, tok_pos, tok_slot, page_table, cos_t, sin_t, H, D, kv_base, rope_cs, rope_sn):
     """Step constants of decode_qkv_rope_append: kv_base [B] int64, rope_cs / rope_sn [B, D] fp16 (written)."""
     B = tok_seq.numel()
