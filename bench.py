@@ -153,28 +153,37 @@ def run_ours(args):
     counters = dict(h2d=0, d2h=0)
 
     if args.config in ("story", "sink"):
-        turns, sink = args.turns, args.config == "sink"
-        inputs = [synthetic_story(rank * 1000 + i) for i in range(n_steps_total)]
+        turns, sink, spg = args.turns, args.config == "sink", max(1, args.stories_per_gpu)
+        # step i of this rank = stories i*spg .. i*spg+spg-1 (spg > 1: their MLLM decode steps are batched, configs[3])
+        inputs = [synthetic_story(rank * 1000 + i) for i in range(n_steps_total * spg)]
         dev_inputs = [(im.to(dev), cap) for im, cap in inputs]
         pinned = [(im.pin_memory(), cap) for im, cap in inputs]
 
+        def run(ims, caps, **kw):
+            if spg == 1:
+                return [pipe.run_story(ims[0], caps[0], turns, sink=sink, **kw)]
+            return pipe.run_stories(ims, caps, turns, sink=sink, **kw)
+
         def step_dev(i):
-            outs = pipe.run_story(dev_inputs[i][0], dev_inputs[i][1], turns, sink=sink)
-            return sum(1 for o in outs if o["has_img_output"])      # a story ends early if a turn emits no image
+            grp = dev_inputs[i * spg:(i + 1) * spg]
+            outs = run([g[0] for g in grp], [g[1] for g in grp])
+            return sum(1 for st in outs for o in st if o["has_img_output"])   # a story ends early if a turn emits no image
 
         def step_e2e(i):
-            im_host, cap = pinned[i]
-            im = im_host.to(dev, non_blocking=True)
-            cap_dev = torch.tensor(cap, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)   # ids travel too
-            counters["h2d"] += im_host.numel() * 2 + cap_dev.numel() * 4
-            outs = pipe.run_story(im, cap, turns, return_images=True, sink=sink)
+            ims, caps = [], []
+            for im_host, cap in pinned[i * spg:(i + 1) * spg]:
+                ims.append(im_host.to(dev, non_blocking=True))
+                cap_dev = torch.tensor(cap, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)   # ids travel too
+                counters["h2d"] += im_host.numel() * 2 + cap_dev.numel() * 4
+                caps.append(cap)
             n = 0
-            for o in outs:
-                if not o["has_img_output"]:
-                    continue
-                n += 1
-                host_img.copy_(o["image"], non_blocking=True)
-                counters["d2h"] += host_img.numel() + len(o["generate_ids"]) * 8
+            for st in run(ims, caps, return_images=True):
+                for o in st:
+                    if not o["has_img_output"]:
+                        continue
+                    n += 1
+                    host_img.copy_(o["image"], non_blocking=True)
+                    counters["d2h"] += host_img.numel() + len(o["generate_ids"]) * 8
             torch.cuda.current_stream().synchronize()
             return n
         unit = "story-turns/s"
@@ -256,8 +265,9 @@ def run_ours(args):
                         f"feature tensor: ResamplerXLV2 + zero-image ViT branch (cached) + {args.denoise_steps} Euler steps CFG 7.5 "
                         f"(UNet batch 2) + VAE decode")
         elif args.config == "sink":
-            workload = (f"configs[3] shape at 1 story per GPU: {args.turns}-turn story in LIVE attention-sink mode (paged KV "
-                        f"kept across turns, sink retention at each eviction, window 8), SDXL {args.denoise_steps} steps")
+            workload = (f"configs[3]: {max(1, args.stories_per_gpu)} stor{'y' if args.stories_per_gpu <= 1 else 'ies'} per GPU "
+                        f"(MLLM decode steps batched over the paged KV cache), {args.turns}-turn stories in LIVE attention-sink mode "
+                        f"(paged KV kept across turns, sink retention at each eviction, window 8), SDXL {args.denoise_steps} steps")
         else:
             workload = ("configs[1]: 10-turn interleaved story, batch=1 per GPU, fp16, 448^2 start image, 64-token caption, "
                         f"64 text tokens + 66-token image run per turn, SDXL 1024^2 {args.denoise_steps} Euler steps CFG 7.5, "
@@ -266,7 +276,7 @@ def run_ours(args):
                     warmup=args.warmup, ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f16", data="synthetic",
                     config=dict(workload=workload, turns_per_step=(args.turns if args.config != "sdxl" else None),
-                                units_counted=int(n_units), stories_per_gpu=1,
+                                units_counted=int(n_units), stories_per_gpu=max(1, args.stories_per_gpu),
                                 parallelism=f"dp{world} (independent replicas, no data-path collective)",
                                 timing="operands (13.2 GB Llama weights per decode step, 5.1 GB UNet) exceed the 126 MB L2; no flush needed",
                                 weights="seeded random, real shapes (no checkpoints offline)",
@@ -656,6 +666,8 @@ def main():
     ap.add_argument("--config", default="story", choices=["story", "sink", "sdxl"])
     ap.add_argument("--turns", type=int, default=None)
     ap.add_argument("--denoise-steps", type=int, default=None)
+    ap.add_argument("--stories-per-gpu", type=int, default=1, help="stories per step per GPU; > 1 batches their MLLM decode "
+                    "steps over the paged KV cache (BASELINE configs[3] uses 4)")
     ap.add_argument("--e2e-steps", type=int, default=6, help="steps of the host-buffer (e2e) leg, <= --steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")

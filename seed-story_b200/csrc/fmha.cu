@@ -281,6 +281,10 @@ int launch_fmha(const FmhaParams& p, cudaStream_t s) {
 
 }  // namespace
 
+int ss_internal_fmha_tc_paged(const void* q, const void* kpool, const void* vpool, void* out, int B, int H, int Lq, int Lk,
+                              int D, long long q_sb, long long q_sl, long long q_sh, long long o_sb, long long o_sl,
+                              long long o_sh, const int* page_table, int max_pages, float scale, int causal,
+                              cudaStream_t stream);
 int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, int B, int H, int Lq, int Lk, int D,
                         long long q_sb, long long q_sl, long long q_sh, long long k_sb, long long k_sl, long long k_sh,
                         long long v_sb, long long v_sl, long long v_sh, long long o_sb, long long o_sl, long long o_sh,
@@ -315,6 +319,15 @@ SS_API int ss_fmha_f16(const void* q, const void* k, const void* v, void* out, i
     // tcgen05 path (S/PV accumulators in TMEM); -1 = layout not expressible as row-matrix views
     const int rc = ss_internal_fmha_tc(q, k, v, out, B, H, Lq, Lk, D, q_sb, q_sl, q_sh, k_sb, k_sl, k_sh, v_sb, v_sl, v_sh,
                                        o_sb, o_sl, o_sh, scale, causal, (cudaStream_t)stream);
+    if (rc >= 0) {
+      if (rc == 0) g_fmha_tc_calls++;
+      return rc;
+    }
+  }
+  if (page_table != nullptr && kv_lens == nullptr && D == 128 && Lq >= 64 && Lk >= fmha_tc_min_lk()) {
+    // paged K/V (the Llama prefill and the 66-token image-run chunk) on the tcgen05 kernel: pages through 3-D TMA maps
+    const int rc = ss_internal_fmha_tc_paged(q, k, v, out, B, H, Lq, Lk, D, q_sb, q_sl, q_sh, o_sb, o_sl, o_sh, page_table,
+                                             max_pages, scale, causal, (cudaStream_t)stream);
     if (rc >= 0) {
       if (rc == 0) g_fmha_tc_calls++;
       return rc;

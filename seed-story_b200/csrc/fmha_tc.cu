@@ -35,6 +35,10 @@ struct FtParams {
   float scale_log2;
   int causal;
   int stages, poly;
+  // paged K/V (the Llama cache: pages [page][H][64][D]): tmK / tmV are 3-D maps (D, 64 tokens, page * H + head) and a
+  // 128-key tile is two pages from this sequence's page-table row
+  const int* page_table;
+  int paged, max_pages;
 };
 
 // 2^x for x <= 0 on the FMA / integer pipes: round-to-nearest split x = xi + xf (magic-number add), a degree-3
@@ -177,10 +181,26 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
         uint8_t* sV = sK + S::KV_BYTES;
         const int krow0 = b * p.k_rows_per_batch + j * FT_BN;
         tc::mbar_expect_tx(&kv_full[s], 2 * S::KV_BYTES);
+        if (p.paged) {
+          // two 64-token pages per tile; a page past the end of the sequence is replaced by the last valid one (its
+          // keys are >= Lk and masked; real data keeps the P V product free of stale-memory NaNs)
+          const int npages = (Lk + 63) >> 6;
 #pragma unroll
-        for (int a = 0; a < D / 64; ++a) {
-          tc::tma_load_2d(sK + a * S::ATOM, &tmK, &kv_full[s], p.k_col0 + h * p.k_col_per_head + a * 64, krow0);
-          tc::tma_load_2d(sV + a * S::ATOM, &tmV, &kv_full[s], p.v_col0 + h * p.v_col_per_head + a * 64, krow0);
+          for (int half = 0; half < 2; ++half) {
+            const int pi = min(2 * j + half, npages - 1);
+            const int row = p.page_table[(size_t)b * p.max_pages + pi] * p.H + h;
+#pragma unroll
+            for (int a = 0; a < D / 64; ++a) {
+              tc::tma_load_3d(sK + a * S::ATOM + half * (64 * 128), &tmK, &kv_full[s], a * 64, 0, row);
+              tc::tma_load_3d(sV + a * S::ATOM + half * (64 * 128), &tmV, &kv_full[s], a * 64, 0, row);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int a = 0; a < D / 64; ++a) {
+            tc::tma_load_2d(sK + a * S::ATOM, &tmK, &kv_full[s], p.k_col0 + h * p.k_col_per_head + a * 64, krow0);
+            tc::tma_load_2d(sV + a * S::ATOM, &tmV, &kv_full[s], p.v_col0 + h * p.v_col_per_head + a * 64, krow0);
+          }
         }
       }
     }
@@ -720,5 +740,48 @@ int ss_internal_fmha_tc(const void* q, const void* k, const void* v, void* out, 
   p.stages = 4;  // K/V ring depth (head_dim 128 uses its own 2-stage layout)
   p.poly = 0;    // exponentials on the MUFU unit (the polynomial split measured no faster, profiles/r1_fmha_experiments.md)
   if (D == 64) return launch_ft<64>(tq, tk, tv, p, B, stream);
+  return launch_ft<128>(tq, tk, tv, p, B, stream);
+}
+
+// Paged variant (head_dim 128): K / V live in a page pool [page][H][64][128]; sequence b's keys are the pages of row b of
+// page_table.  Returns 0 on success, -1 when the layout does not fit (caller falls back to the mma.sync kernel).
+int ss_internal_fmha_tc_paged(const void* q, const void* kpool, const void* vpool, void* out, int B, int H, int Lq, int Lk,
+                              int D, long long q_sb, long long q_sl, long long q_sh, long long o_sb, long long o_sl,
+                              long long o_sh, const int* page_table, int max_pages, float scale, int causal,
+                              cudaStream_t stream) {
+  if (D != 128) return -1;
+  if (q_sl % 8 != 0 || q_sh % 8 != 0 || q_sh * (H - 1) + D > q_sl || !(q_sb == 0 || q_sb == (long long)Lq * q_sl)) return -1;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(kpool) | reinterpret_cast<uintptr_t>(vpool)) & 15) return -1;
+  if (o_sl % 8 != 0 || o_sh % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return -1;
+  CUtensorMap tq, tk, tv;
+  {
+    const uint64_t rows = (uint64_t)(q_sb == 0 ? Lq : (long long)B * Lq);
+    uint64_t dims[2] = {(uint64_t)q_sl, rows}, str[1] = {(uint64_t)q_sl * 2};
+    uint32_t box[2] = {64, 128};
+    if (int e = ss_internal_get_tmap(&tq, q, SS_F16, 2, dims, str, box)) return e;
+  }
+  auto mkp = [&](CUtensorMap* tm, const void* pool) {
+    // (dim within head, token within page, page * H + head); the pool's page count is not known here: the extent is
+    // an upper bound, every access is to a page the table names
+    uint64_t dims[3] = {(uint64_t)D, 64, (uint64_t)1 << 24}, str[2] = {(uint64_t)D * 2, (uint64_t)64 * D * 2};
+    uint32_t box[3] = {64, 64, 1};
+    return ss_internal_get_tmap(tm, pool, SS_F16, 3, dims, str, box);
+  };
+  if (int e = mkp(&tk, kpool)) return e;
+  if (int e = mkp(&tv, vpool)) return e;
+  FtParams p;
+  memset(&p, 0, sizeof(p));
+  p.o = (__half*)out;
+  p.o_sb = o_sb; p.o_sl = o_sl; p.o_sh = o_sh;
+  p.H = H; p.Lq = Lq; p.Lk = Lk;
+  p.q_rows_per_batch = q_sb == 0 ? 0 : Lq;
+  p.q_col_per_head = (int)q_sh;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  p.stages = 4;
+  p.poly = 0;
+  p.page_table = page_table;
+  p.paged = 1;
+  p.max_pages = max_pages;
   return launch_ft<128>(tq, tk, tv, p, B, stream);
 }

@@ -435,6 +435,109 @@ class LlamaEngine:
         return gen, hidden
 
 
+    # ------------------------------------------------------------------ greedy generation, several sequences at once
+    def generate_batch(self, reqs, chunk_image_run=True, use_graph=True):
+        """Greedy generation for len(reqs) <= max_batch independent sequences that share every decode step (one pass over
+        the weights per step for all of them): continuous batching over the paged KV cache — BASELINE configs[3].  The
+        reference ignores padding masks (modeling_llama_xformer.py:289-295, 844), so a sequence's result must not depend on
+        its neighbours: every sequence gets exactly what generate() would give it alone (same kernels row by row).
+
+        reqs[b] = dict(input_ids=list[int], inputs_embeds=[L, hidden] fp16, max_new_tokens=int, schedule=list|None,
+                       past_len=None|int, head=int), or None for an empty slot (sequence b keeps its engine slot b, so
+        a finished story leaves a hole).  Returns [(generated ids, hidden rows, prompt-chunk hidden rows) | None]."""
+        c = self.cfg
+        B = len(reqs)
+        assert 1 <= B <= self.max_batch, f"{B} sequences, engine built for {self.max_batch}"
+        boi, eoi = self.img_ids_h[0], self.img_ids_h[-1]
+        n_img = len(self.img_ids_h) - 2
+        run = [boi] + self.img_ids_h[1:-1] + [eoi]
+        gens, hids, chunk0, Ls, scheds, maxnew = [], [], [], [], [], []
+        for b, r in enumerate(reqs):
+            if r is None:     # an empty slot (a story that has ended): rides along masked, result None
+                self.reset_sequence(b)
+                gens.append([self.eos_id]); hids.append([]); chunk0.append(None); Ls.append(1)
+                scheds.append([-1] * self.max_new); maxnew.append(0)
+                continue
+            ids, emb = list(r["input_ids"]), r["inputs_embeds"]
+            L = len(ids)
+            mx = int(r["max_new_tokens"])
+            past_len, head = r.get("past_len"), int(r.get("head", 0) or 0)
+            n_cached = 0 if past_len is None else int(past_len)
+            if past_len is None:
+                head = 0
+            assert 0 <= head < L, "at least one prompt token must be fed on top of the cache"
+            total = n_cached + (L - head) + mx + 1
+            if mx + 1 > self.max_new or total > self.max_pages * PAGE or L + mx + 1 > c.max_pos:
+                raise _capi.SeedStoryError(f"generate_batch[{b}]({L} prompt + {mx} new tokens on {n_cached} cached) exceeds the "
+                                           f"engine's capacity (max_new {self.max_new}, max_ctx {self.max_pages * PAGE}, "
+                                           f"max_pos {c.max_pos})")
+            if past_len is None:
+                self.reset_sequence(b)
+            else:
+                assert self.seq_len_h[b] == n_cached, (self.seq_len_h[b], n_cached)
+            hn, logits = self.forward_chunk(b, emb[head:], list(range(head, L)))
+            sched = [-1] * self.max_new
+            if r.get("schedule") is not None:
+                sched[:len(r["schedule"])] = r["schedule"]
+            gens.append([self.first_token(logits, int(ids[-1]), sched[0])])
+            hids.append([])
+            chunk0.append(hn)
+            Ls.append(L)
+            scheds.append(sched)
+            maxnew.append(mx)
+        sched_t = torch.tensor(scheds, dtype=torch.int32)
+
+        def active(b):
+            return gens[b][-1] != self.eos_id and len(gens[b]) < maxnew[b]
+
+        def chunkable(b):
+            g, sc = gens[b], scheds[b]
+            return (chunk_image_run and g[-1] == boi and len(g) + n_img + 1 < maxnew[b]
+                    and all(x < 0 for x in sc[len(g):len(g) + n_img + 1]))
+
+        while any(active(b) for b in range(B)):
+            did_chunk = False
+            for b in range(B):
+                if active(b) and chunkable(b):
+                    # the next n_img+1 ids are input-determined (generation.py:23-26): one tensor-core chunk
+                    g = gens[b]
+                    emb = self.embed_tokens(torch.tensor(run))
+                    p0 = Ls[b] + len(g) - 1
+                    hn_c, logits = self.forward_chunk(b, emb, list(range(p0, p0 + len(run))))
+                    hids[b].append(hn_c)
+                    g.extend(run[1:])
+                    g.append(self.first_token(logits, eoi, scheds[b][len(g)] if len(g) < len(scheds[b]) else -1))
+                    did_chunk = True
+            if did_chunk:
+                continue
+            # token-by-token phase for every sequence that is still running; the others ride along masked (done = 1):
+            # their state is not advanced and whatever the step writes for them lands in slots nobody has read yet
+            live = [b for b in range(B) if active(b)]
+            self.begin_decode([gens[b][-1] for b in range(B)], [Ls[b] + len(gens[b]) - 1 for b in range(B)], sched_t[:B])
+            self.n_out[:B].copy_(torch.tensor([len(gens[b]) for b in range(B)], dtype=torch.int32))
+            self.done[:B].copy_(torch.tensor([0 if b in live else 1 for b in range(B)], dtype=torch.int32))
+            while True:
+                self.decode_step(B, use_graph)
+                ids, _ = self.read_step(B)
+                stop = False
+                for b in live:
+                    self.seq_len_h[b] += 1
+                    hids[b].append(self.hist[b, len(gens[b]):len(gens[b]) + 1].clone())
+                    gens[b].append(ids[b])
+                    if not active(b) or chunkable(b):
+                        stop = True      # a sequence ended or reached an image run: re-plan on the host
+                if stop:
+                    break
+        out = []
+        for b in range(B):
+            if reqs[b] is None:
+                out.append(None)
+                continue
+            hidden = torch.cat(hids[b], 0) if hids[b] else torch.empty((0, c.hidden), dtype=torch.float16, device=self.dev)
+            out.append((gens[b], hidden, chunk0[b]))
+        return out
+
+
 class RetainedKV:
     """Engine-native `past_key_values`: "the cache of sequence b exactly as it is now" (typically right after
     LlamaEngine.retain_tokens applied the window / attention-sink policy).  Handing this to generate() costs nothing;

@@ -213,23 +213,95 @@ class StoryPipeline:
             # prompt part (vis_george_sink.py:243-244), append the next tail to the ids (:247-249)
             from . import llama_engine
             eng = self.agent.llm.engine()
-            L_prev = len(input_ids)
-            eng.truncate(0, n_sink + L_prev)
-            input_ids = input_ids + text_ids + self.image_ids
-            while image_embeds.shape[0] > self.window:
-                b0, e0 = input_ids.index(tk.boi), input_ids.index(tk.eoi)        # oldest image, windowed indices
-                cache_len = n_sink + L_prev
-                fresh = llama_engine.sink_retained_slots(cache_len, [(n_sink + b0, n_sink + e0)], n_sink + e0 + 1,
-                                                         n_sink=4 if n_sink == 0 else 0)
-                keep = sorted(set(range(n_sink)) | set(fresh))
-                n_live = cache_len - (n_sink + e0 + 1)
-                input_ids = input_ids[e0 + 1:]
-                image_embeds = image_embeds[1:]
-                L_prev -= e0 + 1
-                eng.retain_tokens(0, keep)            # compaction: slots are contiguous again, sink slots in front
-                n_sink = len(keep) - n_live
+            input_ids, image_embeds, n_sink, L_prev = self._sink_advance(eng, 0, input_ids, text_ids, image_embeds, n_sink)
             model.kv_cache_head = L_prev
             past = llama_engine.RetainedKV(eng, 0)
         if side is not None:
             main.wait_stream(side)               # every image is complete before the caller touches the results
         return outs
+
+    def _sink_advance(self, eng, b, input_ids, text_ids, image_embeds, n_sink):
+        """End-of-turn bookkeeping of the live attention-sink mode for the story in engine slot b: cut the cache back to
+        the prompt, append the next tail to the ids, and when the image window overflows keep only the sink slots
+        (llama_engine.sink_retained_slots) of every evicted image.  Returns (input_ids, image_embeds, n_sink, L_prev)."""
+        from . import llama_engine
+        tk = self.tokenizer
+        L_prev = len(input_ids)
+        eng.truncate(b, n_sink + L_prev)
+        input_ids = input_ids + text_ids + self.image_ids
+        while image_embeds.shape[0] > self.window:
+            b0, e0 = input_ids.index(tk.boi), input_ids.index(tk.eoi)        # oldest image, windowed indices
+            cache_len = n_sink + L_prev
+            fresh = llama_engine.sink_retained_slots(cache_len, [(n_sink + b0, n_sink + e0)], n_sink + e0 + 1,
+                                                     n_sink=4 if n_sink == 0 else 0)
+            keep = sorted(set(range(n_sink)) | set(fresh))
+            n_live = cache_len - (n_sink + e0 + 1)
+            input_ids = input_ids[e0 + 1:]
+            image_embeds = image_embeds[1:]
+            L_prev -= e0 + 1
+            eng.retain_tokens(b, keep)            # compaction: slots are contiguous again, sink slots in front
+            n_sink = len(keep) - n_live
+        return input_ids, image_embeds, n_sink, L_prev
+
+    @torch.no_grad()
+    def run_stories(self, image_tensors, captions, n_turns, decode_images=True, return_images=False, sink=False):
+        """Several independent stories per GPU with their MLLM decode steps BATCHED (continuous batching over the paged KV
+        cache, BASELINE configs[3]: every decode step streams the weights once for all stories); per story the results are
+        those of run_story().  image_tensors: list of [1,3,S,S]; captions: list of id lists.  Story i lives in engine slot
+        i for the whole call (in sink mode its cache stays there across turns).  A story whose turn emits no image ends
+        (gen_george.py:208) and simply stops riding along.  Returns a list (per story) of run_story()-style lists."""
+        from src.models_clm.generation import AutoImageTokenGenerationProcessor
+        tk, dev = self.tokenizer, self.dev
+        S = len(captions)
+        procs = [AutoImageTokenGenerationProcessor(tk, 64)] + self._schedule()
+        res = self.cfg["image"]
+        eng = self.agent.llm.engine(max_batch=S)
+        st = []
+        for i in range(S):
+            st.append(dict(ids=[tk.bos_token_id] + list(captions[i]) + self.image_ids,
+                           emb=self.visual_encoder(image_tensors[i]), outs=[], alive=True, n_sink=0, past_len=None, head=0))
+        for turn in range(n_turns):
+            reqs = []
+            for s_ in st:
+                if not s_["alive"]:
+                    reqs.append(None)        # the story keeps its engine slot; the hole rides along masked
+                    continue
+                ids_t = torch.tensor([s_["ids"]], dtype=torch.long, device=dev)
+                boi = [i for i, t in enumerate(s_["ids"]) if t == tk.boi]
+                eoi = [i for i, t in enumerate(s_["ids"]) if t == tk.eoi]
+                mask = torch.zeros_like(ids_t, dtype=torch.bool)
+                for i in range(s_["emb"].shape[0]):
+                    mask[0, boi[i] + 1:eoi[i]] = True
+                reqs.append(dict(input_ids=ids_t, image_embeds=s_["emb"], ids_cmp_mask=mask,
+                                 embeds_cmp_mask=torch.ones(s_["emb"].shape[0], dtype=torch.bool, device=dev),
+                                 past_len=s_["past_len"], head=s_["head"]))
+            results = self.agent.generate_batch(tk, reqs, logits_processor=procs, max_new_tokens=500, num_img_gen_tokens=64,
+                                                device=dev)
+            for b, (s_, out) in enumerate(zip(st, results)):
+                if out is None:
+                    continue
+                if not out["has_img_output"]:
+                    s_["outs"].append(dict(generate_ids=out["generate_ids"].tolist(), image=None, has_img_output=False))
+                    s_["alive"] = False
+                    continue
+                img = None
+                if decode_images:
+                    img = self.adapter.generate(image_embeds=out["img_gen_feat"], num_inference_steps=self.steps, height=res,
+                                                width=res, output_type="pt", input_image_size=self.cfg["vit"]["image_size"])[0]
+                gen = out["generate_ids"].tolist()
+                s_["outs"].append(dict(generate_ids=gen, image=img if return_images else None, has_img_output=True))
+                s_["emb"] = torch.cat((s_["emb"], out["img_gen_feat"]), dim=0)
+                text_ids = [t for t in gen if t < tk.boi and t != tk.eos_token_id]
+                if not sink:
+                    s_["ids"] = s_["ids"] + text_ids + self.image_ids
+                    while s_["emb"].shape[0] > self.window:
+                        first_eoi = s_["ids"].index(tk.eoi)
+                        s_["ids"] = [tk.bos_token_id] + s_["ids"][first_eoi + 1:]
+                        s_["emb"] = s_["emb"][1:]
+                else:
+                    s_["ids"], s_["emb"], s_["n_sink"], L_prev = self._sink_advance(eng, b, s_["ids"], text_ids, s_["emb"],
+                                                                                    s_["n_sink"])
+                    s_["head"], s_["past_len"] = L_prev, eng.seq_len_h[b]
+            if not any(s_["alive"] for s_ in st):
+                break
+        return [s_["outs"] for s_ in st]

@@ -32,22 +32,11 @@ class ContinuousLVLM(nn.Module):
     def forward(self, *args, **kwargs):
         raise NotImplementedError("training forward (reference models.py:33-96) is outside the inference hot path")
 
-    @torch.no_grad()
-    def generate(self, tokenizer, prompt=None, input_ids=None, image_embeds=None, embeds_cmp_mask=None,
-                 ids_cmp_mask=None, logits_processor=None, num_img_gen_tokens=64, temperature=0.7, num_beams=1,
-                 max_new_tokens=120, top_p=0.5, past_key_values=None, dtype=torch.float16, device='cuda'):
+    def _input_embeds(self, input_ids, image_embeds, embeds_cmp_mask, ids_cmp_mask):
+        """Token embeddings with the resampled image tokens scattered into the <img_i> slots (models.py:127-135)."""
         from seedstory import ops
-        if logits_processor is None:
-            logits_processor = [AutoImageTokenGenerationProcessor(tokenizer=tokenizer,
-                                                                  num_img_gen_tokens=num_img_gen_tokens)]
-        if prompt is not None:
-            input_ids = tokenizer(prompt, return_tensors="pt").input_ids
-        if isinstance(input_ids, list):
-            input_ids = torch.tensor(input_ids)
-        input_ids = input_ids.to(device=device)
         input_embeds = self.llm.get_input_embeddings()(input_ids)
-        bz, sq, dim = input_embeds.shape
-
+        dim = input_embeds.shape[-1]
         if image_embeds is not None:
             assert embeds_cmp_mask is not None and ids_cmp_mask is not None
             image_embeds_lm = self.input_resampler(image_embeds)[embeds_cmp_mask]
@@ -55,18 +44,14 @@ class ContinuousLVLM(nn.Module):
             src = image_embeds_lm.reshape(-1, dim).to(input_embeds.dtype).contiguous()
             assert rows.numel() == src.shape[0], "number of <img_i> slots must match the resampled image tokens"
             ops.scatter_rows(src, rows.to(input_embeds.device), input_embeds.view(-1, dim))
+        return input_embeds
 
-        output = self.llm.generate(input_ids=input_ids, inputs_embeds=input_embeds, output_hidden_states=True,
-                                   return_dict_in_generate=True, logits_processor=logits_processor,
-                                   past_key_values=past_key_values, temperature=temperature, num_beams=num_beams,
-                                   max_new_tokens=max_new_tokens, top_p=top_p, do_sample=False,
-                                   eos_token_id=getattr(tokenizer, "eos_token_id", 2) or 2)
-        output_past_key_values = self.llm.past_key_values
+    def _postprocess(self, tokenizer, input_ids, output, past_key_values, num_img_gen_tokens, output_past_key_values):
+        """models.py:156-221: slice the generated ids, find the last </img>, gather the 64 hidden rows before it, run the
+        output resampler, decode the text."""
         generate_ids = output.sequences[0][input_ids.shape[1]:]
-        boi_token_id = tokenizer.encode(BOI_TOKEN, add_special_tokens=False)[0]
         eoi_token_id = tokenizer.encode(EOI_TOKEN, add_special_tokens=False)[0]
         attn_weights = ()
-
         rows = torch.cat([step[-1] for step in output.hidden_states], dim=1)[0]
         if past_key_values is None:
             # rows of the prompt forward are dropped; row j belongs to the position fed with generated id j (:184-185)
@@ -97,6 +82,54 @@ class ContinuousLVLM(nn.Module):
             'attn_weights': attn_weights,
             'past_key_values': output_past_key_values
         }
+
+    @torch.no_grad()
+    def generate(self, tokenizer, prompt=None, input_ids=None, image_embeds=None, embeds_cmp_mask=None,
+                 ids_cmp_mask=None, logits_processor=None, num_img_gen_tokens=64, temperature=0.7, num_beams=1,
+                 max_new_tokens=120, top_p=0.5, past_key_values=None, dtype=torch.float16, device='cuda'):
+        if logits_processor is None:
+            logits_processor = [AutoImageTokenGenerationProcessor(tokenizer=tokenizer,
+                                                                  num_img_gen_tokens=num_img_gen_tokens)]
+        if prompt is not None:
+            input_ids = tokenizer(prompt, return_tensors="pt").input_ids
+        if isinstance(input_ids, list):
+            input_ids = torch.tensor(input_ids)
+        input_ids = input_ids.to(device=device)
+        input_embeds = self._input_embeds(input_ids, image_embeds, embeds_cmp_mask, ids_cmp_mask)
+        output = self.llm.generate(input_ids=input_ids, inputs_embeds=input_embeds, output_hidden_states=True,
+                                   return_dict_in_generate=True, logits_processor=logits_processor,
+                                   past_key_values=past_key_values, temperature=temperature, num_beams=num_beams,
+                                   max_new_tokens=max_new_tokens, top_p=top_p, do_sample=False,
+                                   eos_token_id=getattr(tokenizer, "eos_token_id", 2) or 2)
+        return self._postprocess(tokenizer, input_ids, output, past_key_values, num_img_gen_tokens,
+                                 self.llm.past_key_values)
+
+    @torch.no_grad()
+    def generate_batch(self, tokenizer, requests, logits_processor=None, num_img_gen_tokens=64, max_new_tokens=120,
+                       device='cuda'):
+        """generate() for several independent stories whose MLLM decode steps are batched (one pass over the weights per
+        step for all of them; BASELINE configs[3]).  requests[b] = dict(input_ids, image_embeds, embeds_cmp_mask,
+        ids_cmp_mask[, past_len, head]) or None for an empty slot; returns the list of generate()'s result dicts (None for
+        empty slots; 'past_key_values' is not materialised)."""
+        if logits_processor is None:
+            logits_processor = [AutoImageTokenGenerationProcessor(tokenizer=tokenizer,
+                                                                  num_img_gen_tokens=num_img_gen_tokens)]
+        ids_l, emb_l, past_lens, heads = [], [], [], []
+        for r in requests:
+            if r is None:       # an empty slot (a story that has ended)
+                ids_l.append(None); emb_l.append(None); past_lens.append(None); heads.append(0)
+                continue
+            ids = r["input_ids"].to(device=device)
+            ids_l.append(ids)
+            emb_l.append(self._input_embeds(ids, r.get("image_embeds"), r.get("embeds_cmp_mask"), r.get("ids_cmp_mask")))
+            past_lens.append(r.get("past_len"))     # live KV reuse: tokens already cached in the story's engine slot
+            heads.append(r.get("head", 0))          # ... and the first prompt token that still has to be fed
+        outs = self.llm.generate_batch(ids_l, emb_l, logits_processor=logits_processor, max_new_tokens=max_new_tokens,
+                                       eos_token_id=getattr(tokenizer, "eos_token_id", 2) or 2, past_lens=past_lens,
+                                       heads=heads)
+        return [None if outs[b] is None else
+                self._postprocess(tokenizer, ids_l[b], outs[b], None if past_lens[b] is None else True, num_img_gen_tokens, None)
+                for b in range(len(outs))]
 
     @classmethod
     def from_pretrained(cls, llm, input_resampler, output_resampler, pretrained_model_path=None, **kwargs):

@@ -108,15 +108,18 @@ class PeftModelForCausalLM(nn.Module):
         print(f"all params: {n}")
 
     # ---------------------------------------------------------------- engine
-    def engine(self, max_new=512, max_ctx=4096):
+    def engine(self, max_new=512, max_ctx=4096, max_batch=1):
         m = self.base_model.model
         dev = m.lm_head.weight.device
-        if self._engine is not None and (self._engine.max_new < max_new
+        if self._engine is not None and (self._engine.max_new < max_new or self._engine.max_batch < max_batch
                                          or self._engine.max_pages * llama_engine.PAGE < max_ctx):
-            self._engine = None  # capacity of the cached engine is too small for this call: rebuild it
+            # capacity of the cached engine is too small for this call: rebuild it (never shrink)
+            max_new, max_batch = max(max_new, self._engine.max_new), max(max_batch, self._engine.max_batch)
+            max_ctx = max(max_ctx, self._engine.max_pages * llama_engine.PAGE)
+            self._engine = None
             torch.cuda.empty_cache()
         if self._engine is None:
-            eng = llama_engine.LlamaEngine(m.engine_config(), dev, max_batch=1, max_ctx=max_ctx, max_new=max_new)
+            eng = llama_engine.LlamaEngine(m.engine_config(), dev, max_batch=max_batch, max_ctx=max_ctx, max_new=max_new)
             layers = []
             for layer in m.model.layers:
                 L = {}
@@ -135,16 +138,8 @@ class PeftModelForCausalLM(nn.Module):
             self._engine = eng
         return self._engine
 
-    # ---------------------------------------------------------------- HF-style generate (greedy only)
-    @torch.no_grad()
-    def generate(self, input_ids=None, inputs_embeds=None, output_hidden_states=False, return_dict_in_generate=False,
-                 logits_processor=None, past_key_values=None, max_new_tokens=120, do_sample=False, num_beams=1,
-                 temperature=None, top_p=None, eos_token_id=2, **kwargs):
-        if do_sample or num_beams != 1:
-            raise NotImplementedError("seedstory_b200 implements the reference's greedy path (do_sample=False, num_beams=1)")
-        assert input_ids.shape[0] == 1, "reference generate is batch-1 (models.py:157)"
-        eng = self.engine(max_new=max(512, max_new_tokens + 2),
-                          max_ctx=max(4096, input_ids.shape[1] + max_new_tokens + 2))
+    def _configure_engine(self, eng, logits_processor, eos_token_id):
+        """Map the `logits_processor=` list of models.py:146-153 onto the engine's device-side implementations."""
         img_ids, schedule, suppress = None, None, []
         for proc in (logits_processor or []):
             if isinstance(proc, ForcedScheduleProcessor):
@@ -161,6 +156,49 @@ class PeftModelForCausalLM(nn.Module):
         elif getattr(eng, "img_ids_h", None) != list(img_ids) or eng.eos_id != eos_token_id:
             eng.set_image_token_ids(img_ids, eos_token_id)
         eng.set_suppress_ids(suppress)
+        return schedule
+
+    @torch.no_grad()
+    def generate_batch(self, input_ids_list, inputs_embeds_list, logits_processor=None, max_new_tokens=120,
+                       eos_token_id=2, past_lens=None, heads=None):
+        """Several independent greedy generations sharing every decode step (LlamaEngine.generate_batch; BASELINE
+        configs[3]: stories batched per rank over the paged KV cache).  Sequence b lives in engine slot b; per sequence
+        the result is what generate() returns for it alone.  Returns a list of GenerateOutput."""
+        B = len(input_ids_list)
+        Lmax = max(int(i.shape[1]) for i in input_ids_list if i is not None)
+        eng = self.engine(max_new=max(512, max_new_tokens + 2), max_ctx=max(4096, Lmax + max_new_tokens + 2), max_batch=B)
+        schedule = self._configure_engine(eng, logits_processor, eos_token_id)
+        reqs = []
+        for b in range(B):
+            if input_ids_list[b] is None:
+                reqs.append(None)
+                continue
+            reqs.append(dict(input_ids=input_ids_list[b][0].tolist(), inputs_embeds=inputs_embeds_list[b][0].to(torch.float16),
+                             max_new_tokens=max_new_tokens, schedule=schedule,
+                             past_len=None if past_lens is None else past_lens[b],
+                             head=0 if heads is None else heads[b]))
+        outs = []
+        for b, res in enumerate(eng.generate_batch(reqs)):
+            if res is None:
+                outs.append(None)
+                continue
+            gen, hidden, chunk_hidden = res
+            seq = torch.tensor([reqs[b]["input_ids"] + gen], dtype=torch.long, device=input_ids_list[b].device)
+            hs = ((chunk_hidden.unsqueeze(0),),) + tuple((hidden[i:i + 1].unsqueeze(0),) for i in range(hidden.shape[0]))
+            outs.append(GenerateOutput(seq, hs, None))
+        return outs
+
+    # ---------------------------------------------------------------- HF-style generate (greedy only)
+    @torch.no_grad()
+    def generate(self, input_ids=None, inputs_embeds=None, output_hidden_states=False, return_dict_in_generate=False,
+                 logits_processor=None, past_key_values=None, max_new_tokens=120, do_sample=False, num_beams=1,
+                 temperature=None, top_p=None, eos_token_id=2, **kwargs):
+        if do_sample or num_beams != 1:
+            raise NotImplementedError("seedstory_b200 implements the reference's greedy path (do_sample=False, num_beams=1)")
+        assert input_ids.shape[0] == 1, "reference generate is batch-1 (models.py:157)"
+        eng = self.engine(max_new=max(512, max_new_tokens + 2),
+                          max_ctx=max(4096, input_ids.shape[1] + max_new_tokens + 2))
+        schedule = self._configure_engine(eng, logits_processor, eos_token_id)
         ids = input_ids[0].tolist()
         if inputs_embeds is None:
             inputs_embeds = self.get_input_embeddings()(input_ids)

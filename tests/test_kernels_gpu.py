@@ -346,24 +346,35 @@ def test_fmha_dense(cuda_dev, D):
     _close(out.view(B, L, H, D), ref, rtol=3e-3, atol=3e-3, what="fmha fused-qkv views")
 
 
-def test_fmha_paged_causal(cuda_dev):
+@pytest.mark.parametrize("Lq,Lk", [(66, 1107), (1041, 1041), (128, 128), (200, 519), (40, 300)])
+def test_fmha_paged_causal(cuda_dev, Lq, Lk):
+    """The Llama prefill (Lq == Lk), the 66-token image-run chunk on a long cache, and odd page counts: paged K/V with
+    the bottom-right causal mask.  Lq >= 64 runs on the tcgen05 kernel (pages through 3-D TMA maps; a 128-key tile = two
+    pages), shorter chunks on the mma.sync kernel; unused pool pages hold NaN so that any read past the table shows."""
     from seedstory import ops
     torch.manual_seed(7)
     H, D = 32, 128
-    Lk, Lq = 1107, 66
     max_pages = 24
-    pool = torch.randn(40, H, 64, D, device=cuda_dev).half()
-    vpool = torch.randn(40, H, 64, D, device=cuda_dev).half()
+    npg = (Lk + 63) // 64
     pt = torch.randperm(40, device=cuda_dev)[:max_pages].int().view(1, max_pages).contiguous()
+    pool = torch.full((40, H, 64, D), float("nan"), device=cuda_dev, dtype=torch.float16)
+    vpool = torch.full_like(pool, float("nan"))
+    used = pt[0, :npg].long()
+    pool[used] = torch.randn(npg, H, 64, D, device=cuda_dev).half()
+    vpool[used] = torch.randn(npg, H, 64, D, device=cuda_dev).half()
     q = torch.randn(1, Lq, H * D, device=cuda_dev).half()
     out = torch.empty_like(q)
+    ops.fmha_path_counts(reset=True)
     ops.fmha(q, pool, vpool, out, 1, H, Lq, Lk, D, (0, H * D, D), (0, 0, 0), (0, 0, 0), (0, H * D, D),
              1.0 / math.sqrt(D), causal=True, page_table=pt)
-    npg = (Lk + 63) // 64
-    k = pool[pt[0, :npg].long()].permute(0, 2, 1, 3).reshape(-1, H, D)[:Lk][None]
-    v = vpool[pt[0, :npg].long()].permute(0, 2, 1, 3).reshape(-1, H, D)[:Lk][None]
+    torch.cuda.synchronize()
+    tc, mma = ops.fmha_path_counts()
+    assert (tc, mma) == ((1, 0) if Lq >= 64 else (0, 1)), (tc, mma)
+    k = pool[used].permute(0, 2, 1, 3).reshape(-1, H, D)[:Lk][None]
+    v = vpool[used].permute(0, 2, 1, 3).reshape(-1, H, D)[:Lk][None]
     ref = _ref_attn(q.view(1, Lq, H, D), k, v, 1.0 / math.sqrt(D), True)
-    _close(out.view(1, Lq, H, D), ref, rtol=3e-3, atol=3e-3, what="fmha paged causal")
+    assert torch.isfinite(out).all()
+    _close(out.view(1, Lq, H, D), ref, rtol=3e-3, atol=3e-3, what=f"fmha paged causal Lq={Lq} Lk={Lk}")
 
 
 def test_groupnorm_and_glue(cuda_dev):

@@ -189,6 +189,39 @@ def test_batched_decode_equals_batch_one(cuda_dev):
         assert batched[b][:n] == alone[:n], (b, batched[b], alone)
 
 
+def test_generate_batch_equals_generate(cuda_dev):
+    """LlamaEngine.generate_batch (continuous batching: shared decode steps, image-run chunks per sequence, sequences
+    ending at different times, an empty slot) returns for every sequence exactly what generate() returns for it alone."""
+    from oracle import llama_oracle as LO
+    torch.manual_seed(3)
+    p = LO.LlamaParams.random(256, 352, 2, 3, 320, lora_r=16, seed=9, std=0.05)
+    img_ids = [300] + list(range(302, 310)) + [301]
+    prompts = [torch.randint(3, 290, (21,)), torch.randint(3, 290, (70,)), None, torch.randint(3, 290, (40,))]
+    # different forced schedules: an image run early, one late followed by EOS, free text only
+    scheds = [[-1] * 3 + [300], [-1] * 9 + [300] + [-1] * 9 + [2], None, [-1] * 5 + [2]]
+    max_new = [30, 40, 0, 30]
+    eng = _engine_from_params(p, cuda_dev, max_batch=4)
+    eng.set_image_token_ids(img_ids, 2)
+    reqs = []
+    for ids, sc, mx in zip(prompts, scheds, max_new):
+        reqs.append(None if ids is None else dict(input_ids=ids.tolist(), inputs_embeds=p.embed[ids].to(cuda_dev, torch.float16),
+                                                  max_new_tokens=mx, schedule=sc))
+    batched = eng.generate_batch(reqs)
+    assert batched[2] is None
+    eng1 = _engine_from_params(p, cuda_dev, max_batch=1)
+    eng1.set_image_token_ids(img_ids, 2)
+    for b, r in enumerate(reqs):
+        if r is None:
+            continue
+        gen, hid, hn = eng1.generate(0, r["input_ids"], r["inputs_embeds"], r["max_new_tokens"], schedule=r["schedule"],
+                                     return_chunk_hidden=True)
+        bg, bh, bhn = batched[b]
+        assert bg == gen, (b, bg, gen)
+        assert torch.equal(bhn, hn), f"sequence {b}: prompt hidden rows differ"
+        assert bh.shape == hid.shape and _rel(bh, hid) < 1e-3, (b, bh.shape, hid.shape)
+    assert 300 in batched[0][0] and 301 in batched[0][0] and batched[1][0][-1] == 2 and batched[3][0][-1] == 2
+
+
 def test_sink_kv_compaction_matches_oracle_with_sliced_past(cuda_dev):
     """Attention-sink mode: after retaining {first 4} U {window around an evicted <img>/</img>} U live tail, the next
     chunk must equal the oracle fed with the correspondingly sliced past_key_values (keys keep their RoPE phase)."""

@@ -136,3 +136,22 @@ def test_story_ends_like_the_reference_when_a_turn_has_no_image(cuda_dev):
     img = torch.randn(1, 3, 56, 56, device=cuda_dev).half()
     outs = pipe.run_story(img, [5, 9, 17], n_turns=3, decode_images=False)
     assert len(outs) == 1 and outs[0]["has_img_output"] is False and outs[0]["generate_ids"][-1] == pipe.tokenizer.eos_token_id
+
+
+def test_batched_stories_equal_single_stories(cuda_dev):
+    """StoryPipeline.run_stories (BASELINE configs[3]: several stories per GPU, MLLM decode steps batched over the paged
+    KV cache) gives every story the tokens and pixels run_story() gives it alone — windowed re-prefill and live sink."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "seed-story_b200", "shims"))
+    from seedstory import story
+    pipe = story.StoryPipeline(device=cuda_dev, cfg=story.TINY, num_inference_steps=2, n_text_tokens=5, window_size=2)
+    g = torch.Generator().manual_seed(21)
+    imgs = [torch.randn(1, 3, 56, 56, generator=g).half().to(cuda_dev) for _ in range(3)]
+    caps = [[5, 9, 17, 33], [7, 7, 21, 40, 41, 42], [100, 3]]
+    for sink in (False, True):
+        batched = pipe.run_stories(imgs, caps, n_turns=4, return_images=True, sink=sink)
+        for i in range(3):
+            alone = pipe.run_story(imgs[i], caps[i], n_turns=4, return_images=True, sink=sink)
+            assert [o["generate_ids"] for o in batched[i]] == [o["generate_ids"] for o in alone], (sink, i)
+            assert all(torch.equal(a["image"], b["image"]) for a, b in zip(batched[i], alone)), (sink, i)
