@@ -97,6 +97,8 @@ class LlamaEngine:
         self._graphs = {}
         self._pinned_ids = torch.zeros(B, dtype=torch.int32).pin_memory()
         self._pinned_done = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.decode_block = 16          # decode steps queued per host sync in generate()
+        self._pinned_blk = torch.zeros(64, dtype=torch.int32).pin_memory()
 
     # ------------------------------------------------------------------ weights
     def load_weights(self, embed, layers, norm, lm_head, lora_scaling=2.0):
@@ -334,6 +336,14 @@ class LlamaEngine:
         torch.cuda.current_stream().synchronize()
         return self._pinned_ids[:B].tolist(), self._pinned_done[:B].tolist()
 
+    def read_block(self, start, k):
+        """Ids emitted by the last k queued decode steps of sequence 0 (fewer than k if EOS stopped it): ONE host sync."""
+        self._pinned_blk[:k].copy_(self.out_ids[0, start:start + k], non_blocking=True)
+        self._pinned_ids[:1].copy_(self.n_out[:1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n = int(self._pinned_ids[0]) - start
+        return self._pinned_blk[:n].tolist()
+
     def first_token(self, logits, last_id, sched0=-1):
         """Processor + argmax on prefill logits (same kernel as the decode step)."""
         last = torch.tensor([last_id], dtype=torch.int32, device=self.dev)
@@ -407,10 +417,13 @@ class LlamaEngine:
         n_img = len(self.img_ids_h) - 2
         armed = False
         while gen[-1] != self.eos_id and len(gen) < max_new_tokens:
-            if chunk_image_run and gen[-1] == boi and len(gen) + n_img + 1 < max_new_tokens \
-                    and all(s < 0 for s in sched[len(gen):len(gen) + n_img + 1]):
-                # the next n_img+1 ids are input-determined (generation.py:23-26): feed [BOI, IMG_0.., EOI] as ONE chunk
-                run = [boi] + self.img_ids_h[1:-1] + [eoi]
+            # inside an image run the remaining ids are input-determined (generation.py:23-26): feed what is left of
+            # [<img>, IMG_0.., </img>] as ONE chunk (normally the whole run: the last id is <img>)
+            i_run = self.img_ids_h.index(gen[-1]) if gen[-1] in self.img_ids_h[:-1] else -1
+            n_left = len(self.img_ids_h) - 1 - i_run
+            if chunk_image_run and i_run >= 0 and len(gen) + n_left < max_new_tokens \
+                    and all(s < 0 for s in sched[len(gen):len(gen) + n_left]):
+                run = self.img_ids_h[i_run:]
                 emb = self.embed_tokens(torch.tensor(run))
                 p0 = L + len(gen) - 1
                 hn_c, logits = self.forward_chunk(b, emb, list(range(p0, p0 + len(run))))
@@ -424,11 +437,26 @@ class LlamaEngine:
                 self.begin_decode([gen[-1]], [L + len(gen) - 1], sched_t)
                 self.n_out[:1].fill_(len(gen))
                 armed = True
-            self.decode_step(1, use_graph)
-            ids, _ = self.read_step(1)
-            self.seq_len_h[b] += 1
-            hid_rows.append(self.hist[0, len(gen):len(gen) + 1].clone())
-            gen.append(ids[0])
+            # a BLOCK of decode steps is queued before the host looks (one sync per block, not per token): the device
+            # applies the processor, the schedule and the EOS stop itself (after EOS the steps are no-ops on the state).
+            # A block ends at the next scheduled id (it may be <img>: the run then takes the chunk path) and at
+            # max_new_tokens; a free-running <img> inside a block is followed by forced query ids decoded one by one,
+            # exactly as the reference decodes them, and the rest of the run is chunked above.
+            start = len(gen)
+            k = min(self.decode_block, max_new_tokens - start)
+            for j in range(start, start + k):
+                if sched[j] >= 0:
+                    k = j - start + 1
+                    break
+            for _ in range(k):
+                self.decode_step(1, use_graph)
+            ids = self.read_block(start, k)
+            n = len(ids)
+            self.seq_len_h[b] += n
+            hid_rows.append(self.hist[0, start:start + n].clone())
+            gen.extend(ids)
+            if n < k:
+                assert gen[-1] == self.eos_id, (gen[-4:], n, k)
         hidden = torch.cat(hid_rows, 0) if hid_rows else torch.empty((0, c.hidden), dtype=torch.float16, device=self.dev)
         if return_chunk_hidden:
             return gen, hidden, hn
