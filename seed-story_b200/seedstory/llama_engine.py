@@ -198,7 +198,8 @@ class LlamaEngine:
         if n:
             ops.kv_gather_tokens(self.k_pages, self.v_pages, old_pages.to(self.dev), new_pages.to(self.dev),
                                  torch.tensor(keep, **i32), self.cfg.heads, self.cfg.head_dim)
-        torch.cuda.current_stream().synchronize()  # old pages are recycled below
+        # the old pages go back to the pool without a host sync: every later writer of those pages is queued on this
+        # stream behind the gather that reads them (the same argument as in truncate())
         self.free_pages.extend(old_pages.tolist())
         self.page_table_h[b].zero_()
         self.page_table_h[b, :need] = new_pages
