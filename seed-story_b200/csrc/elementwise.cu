@@ -252,9 +252,10 @@ constexpr int GN_TICKETS = 64;
 static inline void groupnorm_geometry(int N, int HW, int C, int* block, int* chunks, int* pix_per_cta) {
   const int vecs = C / 8;
   *block = vecs <= 256 ? vecs * (256 / vecs) : vecs;
-  // ~8 CTAs per SM over the batch; a thread walks its pixels serially (4 loads in flight), so short walks matter more
-  // than few CTAs: the 32x32x1280 level used to run 64 CTAs x 32 dependent pixels (31 us for 5 MB)
-  int ch = (148 * 8 + N - 1) / N;
+  // a thread walks its pixels serially (4 loads in flight), so the walks must stay short: the 32x32x1280 level used to
+  // run 64 CTAs x 32 dependent pixels (31 us for 5 MB)
+  // 4 CTAs per SM over the batch (swept 2 / 4 / 8 / 12 on the UNet step: 21.35 / 21.10 / 21.27 / 21.42 ms)
+  int ch = (148 * 4 + N - 1) / N;
   int ppc = (HW + ch - 1) / ch;
   if (ppc < 8) ppc = 8;
   *pix_per_cta = ppc;
