@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — story-turns/sec of the SEED-Story interleaved inference hot path on B200 (contract in the task brief).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config story|sink|sdxl]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config story|sink|sdxl] [--stories-per-gpu S]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
 --config story (default; BASELINE.json configs[1], and configs[2] when launched on N GPUs): a *step* is one 10-turn
@@ -9,14 +9,16 @@ synthetic StoryStream-shaped story per GPU: start image 448x448, 64-token captio
 forced <img>, 64 image queries, </img>, EOS, then one SDXL 1024x1024 image (Euler, 50 steps, CFG 7.5, seed 42) decoded
 by the VAE; window of 8 images.  Stories are independent, so N GPUs run N stories data-parallel with no data-path
 collective ("scaling": "weak").
---config sink  (configs[3] shape at batch 1 per GPU): 25-turn stories in LIVE multimodal attention-sink mode (paged KV
-kept across turns, sink retention at every eviction).
+--config sink  (configs[3]): 25-turn stories in LIVE multimodal attention-sink mode (paged KV kept across turns, sink
+retention at every eviction); --stories-per-gpu 4 runs four stories per GPU with their MLLM decode steps batched over
+the paged KV cache (continuous batching; a step is then 4 stories, `value` still counts story-turns).
 --config sdxl  (configs[4]): a step is one SDXL de-tokenizer image (30 Euler steps, CFG, VAE decode) per GPU from a
 256x4096 image-feature tensor; metric = images/s.
 
   value : metric with the inputs already on the device, results left on the device
   e2e   : the same steps through the reference-facing API (src.* drop-ins) from HOST buffers: pinned inputs copied H2D
-          inside the timed region, every turn's token ids and 1024x1024 uint8 image copied D2H
+          inside the timed region, every turn's token ids and 1024x1024 uint8 image copied D2H (bounded to --e2e-steps,
+          default 6, of the same steps so that the default run stays within minutes)
   roofline            : the dominant kernel family (tcgen05 GEMM / implicit-GEMM conv of the UNet): every launch type of
                         one UNet step timed live as 10 back-to-back launches in a CUDA graph (CUDA events), weighted by
                         its count; peak = BURST bf16 (kernels timed in isolation)
