@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
   if (*tmem_ptr_smem != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
   // TMEM columns: S0 | S1 (128 each) | O accumulator (D columns at 256) | L = row sums of P (16 columns at 384)
-  const int nst = min(S::STAGES, p.stages);  // SS_FMHA_STAGES caps the K/V ring (A/B aid)
+  const int nst = min(S::STAGES, p.stages);  // K/V ring depth (p.stages is fixed by the host launcher)
   constexpr int PB = S::P_BUFS;
   const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 256, tmem_L = tmem_base + 384;
 
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fmha_tc_kernel(const __grid_con
           const float xa = fmaf(__uint_as_float(cur[g * 8 + 2 * i]), p.scale_log2, -msc);
           const float xb = fmaf(__uint_as_float(cur[g * 8 + 2 * i + 1]), p.scale_log2, -msc);
           // fp32 MUFU.EX2 (the packed-half form issues as two MUFU.EX2.F16 and is no faster); `poly` of every
-          // 4 pairs may take an FMA-pipe polynomial instead (SS_FMHA_POLY, 0 = all on the special-function unit)
+          // 4 pairs may take an FMA-pipe polynomial instead (p.poly, fixed at 0 by the host launcher = all on the special-function unit)
           float ea, eb;
           if (i < poly) {
             ea = exp2_fma(xa);
