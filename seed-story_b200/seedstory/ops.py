@@ -267,16 +267,16 @@ class FoldedLN:
     """A LayerNorm folded into the Linear that consumes it (ss_gemm_tn_ln): y = LN(x; gamma, beta, eps) W^T + b is
     evaluated as rstd (x W''^T) + shift on the RAW rows x, with the row-centred weights
     W''[n,k] = gamma[k] W[n,k] - mean_k(gamma[k] W[n,k]) — x W''^T equals (x - mean(x)) (gamma (.) W)^T, the mean
-    subtraction rides on the contraction — and shift[n] = sum_k beta[k] W[n,k] + b[n] (load-time packing, fp32 math,
+    subtraction rides on the contraction — and shift[n] = sum_k beta[k] W[n,k] + b[n] (load-time packing, fp64 math,
     one rounding to the compute type)."""
 
     def __init__(self, w, gamma, beta, eps, bias=None):
-        wf = w.float()
-        wg = wf * gamma.float()[None, :]
+        wf = w.double()                                   # load-time packing: fp64 math, one rounding to the compute type
+        wg = wf * gamma.double()[None, :]
         self.w = (wg - wg.mean(dim=1, keepdim=True)).to(w.dtype).contiguous()
-        shift = wf @ beta.float()
+        shift = wf @ beta.double()
         if bias is not None:
-            shift = shift + bias.float()
+            shift = shift + bias.double()
         self.shift = shift.to(w.dtype).contiguous()
         self.eps = float(eps)
 

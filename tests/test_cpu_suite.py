@@ -305,3 +305,36 @@ def test_hydra_shim_instantiates_reference_style_configs(tmp_path, monkeypatch):
     assert hydra.utils.instantiate(OmegaConf.load(tmp_path / "id.yaml")).encode_image_embeds(3) == 3
     lc = hydra.utils.instantiate(OmegaConf.load(tmp_path / "lora.yaml"))
     assert lc.r == 16 and lc.target_modules == ["q_proj", "v_proj"]
+
+
+def test_folded_layernorm_packing_is_exact_algebra():
+    """ops.FoldedLN (host packing for ss_gemm_tn_ln): with the row-centred weights W'' the plain product x W''^T already
+    carries the mean subtraction, so rstd * (x W''^T) + shift equals LayerNorm(x) W^T + b."""
+    from seedstory import ops
+    g = torch.Generator().manual_seed(0)
+    M, K, N = 37, 96, 40
+    x = torch.randn(M, K, generator=g, dtype=torch.float64) * 1.7 + 0.9        # rows with a non-zero mean
+    w = torch.randn(N, K, generator=g, dtype=torch.float64) * 0.1
+    gamma, beta = torch.randn(K, generator=g, dtype=torch.float64), torch.randn(K, generator=g, dtype=torch.float64)
+    bias = torch.randn(N, generator=g, dtype=torch.float64)
+    f = ops.FoldedLN(w, gamma, beta, 1e-5, bias=bias)
+    assert f.w.dtype == w.dtype and float(f.w.sum(dim=1).abs().max()) < 1e-9     # every row sums to zero
+    var = x.var(dim=1, unbiased=False, keepdim=True)
+    got = (x @ f.w.t()) * torch.rsqrt(var + 1e-5) + f.shift
+    ref = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-5) @ w.t() + bias
+    assert torch.allclose(got, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_rope_row_interleave_layout():
+    """ops.interleave_rope_rows: inside every q and k head row 2i holds dim i and row 2i+1 dim i + D/2 (the rotary pair of
+    apply_rotary_pos_emb, modeling_llama_xformer.py:165-173, in neighbouring rows); v rows keep their order."""
+    from seedstory import ops
+    H, D, K = 3, 8, 5
+    w = torch.arange(3 * H * D, dtype=torch.float32)[:, None].repeat(1, K)      # row r is filled with r
+    il = ops.interleave_rope_rows(w, H, D)
+    for sec in range(2):
+        for h in range(H):
+            base = sec * H * D + h * D
+            for i in range(D // 2):
+                assert il[base + 2 * i, 0] == base + i and il[base + 2 * i + 1, 0] == base + i + D // 2
+    assert torch.equal(il[2 * H * D:], w[2 * H * D:])
