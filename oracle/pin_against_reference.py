@@ -347,10 +347,111 @@ def pin_sink_kv_reuse():
                os.path.join(GOLD, "sink_kv_reuse.pt"))
 
 
+def pin_lvlm_generate():
+    """ContinuousLVLM.generate (src/models_clm/models.py:98-221) — the reference's OWN class, run on CPU around a fake
+    `llm` that replays a fixed generation (ids + per-step hidden states), so that everything the method itself computes
+    is pinned: the scatter of the resampled image tokens into the <img_i> slots (:127-135), the slicing of the
+    generated ids, the search for the LAST </img> in both branches (past_key_values None / given, :182-197), the 64
+    hidden rows handed to the output resampler, has_img_output / num_gen_imgs.  Freezes tests/golden/lvlm_generate.pt
+    and checks the oracle's lvlm_postprocess / lvlm_postprocess_past against it."""
+    sys.path.insert(0, REF)
+    import types
+    from src.models_clm.models import ContinuousLVLM
+    E, n_q = 32, 8                      # hidden width, image tokens per image (num_img_gen_tokens)
+    boi, eoi, img0 = 300, 301, 302
+    img_ids = [boi] + [img0 + i for i in range(n_q)] + [eoi]
+    g = torch.Generator().manual_seed(23)
+
+    class _Tok:
+        eos_token_id = 2
+
+        def encode(self, text, add_special_tokens=False):
+            return {"<img>": [boi], "</img>": [eoi]}.get(text, img_ids)
+
+        def decode(self, ids, skip_special_tokens=False):
+            return " ".join(str(int(i)) for i in ids)
+
+    class _Resampler(torch.nn.Module):          # deterministic stand-ins with the resamplers' shapes
+        def __init__(self, n_out, scale):
+            super().__init__()
+            self.n_out, self.scale = n_out, scale
+
+        def forward(self, x):
+            return x[:, :self.n_out] * self.scale + 0.25
+
+    class _FakeLLM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(320, E)
+            self.past_key_values = "kv-of-this-call"
+            self.replay = None
+
+        def get_input_embeddings(self):
+            return self.emb
+
+        def generate(self, input_ids=None, inputs_embeds=None, **kw):
+            gen, hs = self.replay
+            self.seen_embeds = inputs_embeds.detach().clone()
+            return types.SimpleNamespace(sequences=torch.cat([input_ids, torch.tensor([gen])], dim=1), hidden_states=hs,
+                                         attentions=None)
+
+    llm = _FakeLLM()
+    model = ContinuousLVLM(llm, _Resampler(n_q, 2.0), _Resampler(2 * n_q, -1.5)).eval()
+    tok = _Tok()
+    prompt = [1, 11, 12] + img_ids + [13, 14] + img_ids          # two input images
+    ids = torch.tensor([prompt])
+    mask = torch.zeros_like(ids, dtype=torch.bool)
+    b = [i for i, t in enumerate(prompt) if t == boi]
+    e = [i for i, t in enumerate(prompt) if t == eoi]
+    for k in range(2):
+        mask[0, b[k] + 1:e[k]] = True
+    image_embeds = torch.randn(3, 2 * n_q, E, generator=g)        # three candidate images, the middle one unused
+    emb_mask = torch.tensor([True, False, True])
+    cases = {}
+    gens = {"one_run": [21, 22] + img_ids + [2],
+            "two_runs_last_wins": [21] + img_ids + [22, 23] + img_ids + [2],
+            "no_image": [21, 22, 23, 2]}
+    L = len(prompt)
+    for name, gen in gens.items():
+        for branch in ("none", "past"):
+            T = len(gen)
+            # HF hands back one tuple per step; the last element of each is the final hidden state of that forward:
+            # step 0 covers the fed prompt (all of it without a past, its tail [text, <img>..</img>] of 12 tokens with one —
+            # the prompt tail of the sink script ends in an image, which the KV branch's </img> search can find: with no
+            # new image generated the reference reports the PROMPT's last image, a quirk this fixture pins), then one row
+            # per step
+            fed0 = L if branch == "none" else 12
+            hs = ((torch.randn(1, fed0, E, generator=g),),) + tuple((torch.randn(1, 1, E, generator=g),) for _ in range(T - 1))
+            llm.replay = (gen, hs)
+            with torch.no_grad():
+                out = model.generate(tokenizer=tok, input_ids=ids.clone(), image_embeds=image_embeds, embeds_cmp_mask=emb_mask,
+                                     ids_cmp_mask=mask, num_img_gen_tokens=n_q, max_new_tokens=64,
+                                     past_key_values=None if branch == "none" else "sliced-cache", device="cpu")
+            rows = torch.cat([h[-1] for h in hs], dim=1)[0]
+            if branch == "none":
+                feats = LO.lvlm_postprocess(gen, rows[L:], eoi, n_q)
+            else:
+                feats = LO.lvlm_postprocess_past(prompt + gen, rows, eoi, n_q)
+            if out["has_img_output"]:
+                ref_in = (out["img_gen_feat"] - 0.25) / -1.5                     # undo the stand-in output resampler
+                assert feats is not None and _maxdiff(feats[None], ref_in) < 1e-6, (name, branch)
+            else:
+                assert feats is None and out["img_gen_feat"] is None, (name, branch)
+            assert out["generate_ids"].tolist() == gen and out["past_key_values"] == "kv-of-this-call"
+            cases[f"{name}/{branch}"] = dict(gen=gen, hidden_states=[h[-1] for h in hs], has_img_output=out["has_img_output"],
+                                             num_gen_imgs=out["num_gen_imgs"], img_gen_feat=out["img_gen_feat"],
+                                             text=out["text"], input_embeds=llm.seen_embeds)
+    print("ContinuousLVLM.generate pinned:", ", ".join(cases))
+    torch.save({"E": E, "n_q": n_q, "boi": boi, "eoi": eoi, "img_ids": img_ids, "prompt": prompt, "ids_cmp_mask": mask,
+                "image_embeds": image_embeds, "embeds_cmp_mask": emb_mask, "emb_weight": llm.emb.weight.detach().clone(),
+                "cases": cases}, os.path.join(GOLD, "lvlm_generate.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     pin_llama()
     pin_greedy_loop()
     pin_vision()
     pin_sink_kv_reuse()
+    pin_lvlm_generate()
     print("golden vectors written to", GOLD)

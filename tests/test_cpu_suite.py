@@ -338,3 +338,63 @@ def test_rope_row_interleave_layout():
             for i in range(D // 2):
                 assert il[base + 2 * i, 0] == base + i and il[base + 2 * i + 1, 0] == base + i + D // 2
     assert torch.equal(il[2 * H * D:], w[2 * H * D:])
+
+
+def _lvlm_golden():
+    import os
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "lvlm_generate.pt"), weights_only=False)
+
+
+def test_oracle_lvlm_postprocess_matches_reference_golden():
+    """oracle.llama_oracle.lvlm_postprocess / lvlm_postprocess_past vs the reference's own ContinuousLVLM.generate
+    (golden made by oracle/pin_against_reference.py::pin_lvlm_generate around a fake llm): both branches, one / two image
+    runs (the last </img> wins), no image, and the KV branch's quirk of finding the prompt tail's </img>."""
+    from oracle import llama_oracle as LO
+    g = _lvlm_golden()
+    L, n_q, eoi = len(g["prompt"]), g["n_q"], g["eoi"]
+    for name, c in g["cases"].items():
+        rows = torch.cat(c["hidden_states"], dim=1)[0]
+        if name.endswith("/none"):
+            feats = LO.lvlm_postprocess(c["gen"], rows[L:], eoi, n_q)
+        else:
+            feats = LO.lvlm_postprocess_past(g["prompt"] + c["gen"], rows, eoi, n_q)
+        assert (feats is not None) == c["has_img_output"], name
+        if feats is not None:
+            assert torch.allclose(feats[None][:, :2 * n_q] * -1.5 + 0.25, c["img_gen_feat"], atol=1e-6), name
+    assert g["cases"]["no_image/past"]["has_img_output"] and not g["cases"]["no_image/none"]["has_img_output"]
+
+
+def test_dropin_lvlm_postprocess_matches_reference_golden():
+    """The drop-in ContinuousLVLM's post-processing (same dict as models.py:213-221) on the golden's replayed generation:
+    generate_ids, has_img_output, num_gen_imgs, the rows handed to the output resampler and the decoded text."""
+    import types
+    from src.models_clm.models import ContinuousLVLM
+    g = _lvlm_golden()
+    n_q = g["n_q"]
+
+    class _Tok:
+        def encode(self, text, add_special_tokens=False):
+            return {"<img>": [g["boi"]], "</img>": [g["eoi"]]}.get(text, g["img_ids"])
+
+        def decode(self, ids, skip_special_tokens=False):
+            return " ".join(str(int(i)) for i in ids)
+
+    class _Out(torch.nn.Module):
+        def forward(self, x):
+            return x[:, :2 * n_q] * -1.5 + 0.25
+
+    model = ContinuousLVLM.__new__(ContinuousLVLM)
+    torch.nn.Module.__init__(model)
+    model.output_resampler = _Out()
+    ids = torch.tensor([g["prompt"]])
+    for name, c in g["cases"].items():
+        out = types.SimpleNamespace(sequences=torch.cat([ids, torch.tensor([c["gen"]])], dim=1),
+                                    hidden_states=tuple((h,) for h in c["hidden_states"]), attentions=None)
+        res = model._postprocess(_Tok(), ids, out, None if name.endswith("/none") else "cache", n_q, "kv")
+        assert res["generate_ids"].tolist() == c["gen"] and res["text"] == c["text"], name
+        assert res["has_img_output"] == c["has_img_output"] and res["num_gen_imgs"] == c["num_gen_imgs"], name
+        assert res["past_key_values"] == "kv" and res["attn_weights"] == ()
+        if c["has_img_output"]:
+            assert torch.allclose(res["img_gen_feat"], c["img_gen_feat"], atol=1e-6), name
+        else:
+            assert res["img_gen_feat"] is None

@@ -326,3 +326,37 @@ def test_kv_reuse_equals_full_prefill_and_truncate(cuda_dev):
     e2.truncate(0, 70)
     hn_tail, lg_tail = e2.forward_chunk(0, emb[70:], list(range(70, 90)))
     assert _rel(hn_tail, hn_full[70:]) < 5e-3 and _rel(lg_tail, lg_full) < 5e-3
+
+
+def test_dropin_lvlm_input_embeds_match_reference_golden(cuda_dev):
+    """ContinuousLVLM._input_embeds (token embeddings with the resampled image tokens scattered into the <img_i> slots by
+    ss_scatter_rows) vs what the reference's own generate() handed to llm.generate (models.py:127-135; golden
+    lvlm_generate.pt: three candidate images of which embeds_cmp_mask selects two)."""
+    import os
+    from src.models_clm.models import ContinuousLVLM
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "lvlm_generate.pt"), weights_only=False)
+    n_q = g["n_q"]
+
+    class _In(torch.nn.Module):
+        def forward(self, x):
+            return x[:, :n_q] * 2.0 + 0.25
+
+    class _LLM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding.from_pretrained(g["emb_weight"].half()).to(cuda_dev)
+
+        def get_input_embeddings(self):
+            return self.emb
+
+    model = ContinuousLVLM.__new__(ContinuousLVLM)
+    torch.nn.Module.__init__(model)
+    model.llm, model.input_resampler = _LLM(), _In()
+    ids = torch.tensor([g["prompt"]], device=cuda_dev)
+    got = model._input_embeds(ids, g["image_embeds"].half().to(cuda_dev), g["embeds_cmp_mask"].to(cuda_dev),
+                              g["ids_cmp_mask"].to(cuda_dev))
+    ref = g["cases"]["one_run/none"]["input_embeds"]
+    assert got.shape == ref.shape and _rel(got, ref) < 2e-3, _rel(got, ref)
+    # rows outside the <img_i> slots are the plain token embeddings, bit for bit
+    keep = ~g["ids_cmp_mask"][0]
+    assert torch.equal(got[0, keep.to(cuda_dev)].cpu(), g["emb_weight"].half()[torch.tensor(g["prompt"])][keep])
