@@ -357,6 +357,7 @@ def pin_lvlm_generate():
     sys.path.insert(0, REF)
     import types
     from src.models_clm.models import ContinuousLVLM
+    torch.manual_seed(23)               # the fake llm's nn.Embedding initialises from the global generator
     E, n_q = 32, 8                      # hidden width, image tokens per image (num_img_gen_tokens)
     boi, eoi, img0 = 300, 301, 302
     img_ids = [boi] + [img0 + i for i in range(n_q)] + [eoi]
