@@ -347,6 +347,30 @@ def pin_sink_kv_reuse():
                os.path.join(GOLD, "sink_kv_reuse.pt"))
 
 
+def pin_transform():
+    """src/processer/transforms.py:4-47 (row a1): the reference's own get_transform on a seeded 300x400 RGB image, every
+    type x keep_ratio at 448 (and the 'sd' type at 1024).  The full outputs are megabytes; the golden keeps a 16x16
+    crop, the sum and the absolute sum of each (tests/golden/transform.pt)."""
+    sys.path.insert(0, REF)
+    import importlib.util
+    import numpy as np
+    from PIL import Image
+    spec = importlib.util.spec_from_file_location("ref_transforms", os.path.join(REF, "src", "processer", "transforms.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    px = np.random.RandomState(5).randint(0, 256, (300, 400, 3), dtype=np.uint8)
+    img = Image.fromarray(px)
+    out = {}
+    for typ, size in (("clip", 448), ("clipa", 448), ("sd", 448), ("sd", 1024)):
+        for keep in (False, True):
+            t = ref.get_transform(type=typ, image_size=size, keep_ratio=keep)(img)
+            assert tuple(t.shape) == (3, size, size)
+            out[f"{typ}/{size}/{int(keep)}"] = dict(crop=t[:, 200:216, 200:216].clone(), sum=float(t.double().sum()),
+                                                   abs_sum=float(t.double().abs().sum()))
+    print("get_transform pinned:", ", ".join(out))
+    torch.save({"pixels_seed": 5, "pixels_shape": (300, 400, 3), "cases": out}, os.path.join(GOLD, "transform.pt"))
+
+
 def pin_lvlm_generate():
     """ContinuousLVLM.generate (src/models_clm/models.py:98-221) — the reference's OWN class, run on CPU around a fake
     `llm` that replays a fixed generation (ids + per-step hidden states), so that everything the method itself computes
@@ -454,5 +478,6 @@ if __name__ == "__main__":
     pin_greedy_loop()
     pin_vision()
     pin_sink_kv_reuse()
+    pin_transform()
     pin_lvlm_generate()
     print("golden vectors written to", GOLD)

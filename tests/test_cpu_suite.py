@@ -398,3 +398,23 @@ def test_dropin_lvlm_postprocess_matches_reference_golden():
             assert torch.allclose(res["img_gen_feat"], c["img_gen_feat"], atol=1e-6), name
         else:
             assert res["img_gen_feat"] is None
+
+
+def test_dropin_transform_matches_reference_golden():
+    """Row a1: the drop-in get_transform vs the reference's own (golden transform.pt: every type x keep_ratio on a seeded
+    300x400 image; a 16x16 crop plus the sum and absolute sum of the full output)."""
+    import os
+    import numpy as np
+    from PIL import Image
+    from src.processer.transforms import get_transform
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "transform.pt"), weights_only=False)
+    px = np.random.RandomState(g["pixels_seed"]).randint(0, 256, g["pixels_shape"], dtype=np.uint8)
+    img = Image.fromarray(px)
+    for name, c in g["cases"].items():
+        typ, size, keep = name.split("/")
+        t = get_transform(type=typ, image_size=int(size), keep_ratio=bool(int(keep)))(img)
+        assert torch.equal(t[:, 200:216, 200:216], c["crop"]), name
+        assert abs(float(t.double().sum()) - c["sum"]) < 1e-6 * max(1.0, abs(c["sum"])), name
+        assert abs(float(t.double().abs().sum()) - c["abs_sum"]) < 1e-6 * c["abs_sum"], name
+    with pytest.raises(NotImplementedError):
+        get_transform(type="other")
