@@ -347,6 +347,78 @@ def pin_sink_kv_reuse():
                os.path.join(GOLD, "sink_kv_reuse.pt"))
 
 
+def _install_diffusers_stub():
+    """src/models_ipa/adapter_modules.py imports pipeline / LoRA classes from diffusers at module level (:6-22); diffusers is
+    not installed here.  Empty stand-ins are enough to IMPORT the file: the method pinned below (get_image_embeds) touches
+    none of them."""
+    import types
+    if "diffusers" in sys.modules:
+        return
+    d = types.ModuleType("diffusers")
+    for n in ("StableDiffusionPipeline", "StableDiffusionXLPipeline", "StableDiffusionXLInstructPix2PixPipeline",
+              "StableDiffusionInstructPix2PixPipeline"):
+        setattr(d, n, type(n, (), {}))
+    loaders = types.ModuleType("diffusers.loaders")
+    loaders.LoraLoaderMixin = type("LoraLoaderMixin", (), {})
+    models = types.ModuleType("diffusers.models")
+    lora = types.ModuleType("diffusers.models.lora")
+    lora.LoRALinearLayer = type("LoRALinearLayer", (), {})
+    blocks = types.ModuleType("diffusers.models.unet_2d_blocks")
+    blocks.DownBlock2D = type("DownBlock2D", (), {})
+    d.loaders, d.models, models.lora, models.unet_2d_blocks = loaders, models, lora, blocks
+    sys.modules.update({"diffusers": d, "diffusers.loaders": loaders, "diffusers.models": models,
+                        "diffusers.models.lora": lora, "diffusers.models.unet_2d_blocks": blocks})
+
+
+def pin_adapter_image_embeds():
+    """SDXLAdapter.get_image_embeds / encode_image_embeds (src/models_ipa/adapter_modules.py:387-428, :345-348; row a13) —
+    the reference's OWN methods, called unbound on an object that carries the attributes they use (visual_encoder,
+    discrete_model, resampler): the unconditional branch is the visual encoder run on a ZERO image, concatenated after
+    the conditional embeds, pushed through the identity discrete model and ResamplerXLV2 together, then chunked.  The
+    oracle-side restatement (torch.cat + vision_oracle.resampler_xl_v2 + chunk, as tests/test_fullsize_gpu.py uses it) is
+    checked against it and tests/golden/adapter_image_embeds.pt is frozen."""
+    _install_diffusers_stub()
+    sys.path.insert(0, REF)
+    from src.models_ipa import resampler as RS
+    from src.models_ipa.adapter_modules import SDXLAdapter
+    torch.manual_seed(29)
+    E, n_tok, S = 256, 64, 32      # (sizes the CUDA kernels accept as well: the same golden drives a GPU test of the drop-in)
+
+    class _Encoder(torch.nn.Module):            # stand-in visual encoder: [B,3,S,S] -> [B, n_tok, E], input dependent
+        def __init__(self):
+            super().__init__()
+            self.proj = torch.nn.Linear(3 * S * S // n_tok, E)
+
+        def forward(self, x):
+            return self.proj(x.reshape(x.shape[0], n_tok, -1)) + 0.1
+
+    class _Identity(torch.nn.Module):           # DiscreteModleIdentity.encode_image_embeds (discrete_models.py:120-130)
+        def encode_image_embeds(self, x):
+            return x
+
+    xl_cfg = dict(dim=256, depth=2, dim_head=64, heads=4, num_queries=16, embedding_dim=E, output1_dim=96,
+                  output2_dim=160, ff_mult=4)
+    obj = SDXLAdapter.__new__(SDXLAdapter)
+    torch.nn.Module.__init__(obj)
+    obj.resampler = RS.ResamplerXLV2(**xl_cfg).eval()
+    # the weights already frozen in resampler_xlv2.pt (same configuration): the golden then only carries activations
+    obj.resampler.load_state_dict(torch.load(os.path.join(GOLD, "resampler_xlv2.pt"), weights_only=False)["sd"])
+    obj.visual_encoder = _Encoder().eval()
+    obj.discrete_model = _Identity()
+    obj.image_transform = None
+    feat = torch.randn(1, n_tok, E)
+    with torch.no_grad():
+        pe, ne, pp, npool = obj.get_image_embeds(image_embeds=feat, return_negative=True, image_size=S)
+        zero_emb = obj.visual_encoder(torch.zeros(1, 3, S, S))
+        e, pool = VO.resampler_xl_v2(obj.resampler.state_dict(), torch.cat([feat, zero_emb], 0), depth=2, heads=4)
+    d = max(_maxdiff(pe, e[:1]), _maxdiff(ne, e[1:]), _maxdiff(pp, pool[:1]), _maxdiff(npool, pool[1:]))
+    assert d < 1e-5, d
+    print("SDXLAdapter.get_image_embeds pinned: max diff of the oracle restatement", d)
+    torch.save({"cfg": xl_cfg, "image_size": S, "feat": feat, "zero_embeds": zero_emb, "resampler_sd_from": "resampler_xlv2.pt",
+                "prompt": pe, "negative": ne, "pooled": pp, "negative_pooled": npool},
+               os.path.join(GOLD, "adapter_image_embeds.pt"))
+
+
 def pin_transform():
     """src/processer/transforms.py:4-47 (row a1): the reference's own get_transform on a seeded 300x400 RGB image, every
     type x keep_ratio at 448 (and the 'sd' type at 1024).  The full outputs are megabytes; the golden keeps a 16x16
@@ -479,5 +551,6 @@ if __name__ == "__main__":
     pin_vision()
     pin_sink_kv_reuse()
     pin_transform()
+    pin_adapter_image_embeds()
     pin_lvlm_generate()
     print("golden vectors written to", GOLD)

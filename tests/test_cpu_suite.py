@@ -418,3 +418,18 @@ def test_dropin_transform_matches_reference_golden():
         assert abs(float(t.double().abs().sum()) - c["abs_sum"]) < 1e-6 * c["abs_sum"], name
     with pytest.raises(NotImplementedError):
         get_transform(type="other")
+
+
+def test_oracle_adapter_image_embeds_matches_reference_golden():
+    """Row a13: the oracle-side restatement of SDXLAdapter.get_image_embeds (conditional embeds + visual encoder of a ZERO
+    image, one ResamplerXLV2 pass over both, chunk) vs the reference's own method (golden adapter_image_embeds.pt)."""
+    import os
+    from oracle import vision_oracle as VO
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "adapter_image_embeds.pt"), weights_only=False)
+    g["resampler_sd"] = torch.load(os.path.join(os.path.dirname(__file__), "golden", g["resampler_sd_from"]),
+                                   weights_only=False)["sd"]
+    with torch.no_grad():
+        e, pool = VO.resampler_xl_v2(g["resampler_sd"], torch.cat([g["feat"], g["zero_embeds"]], 0), g["cfg"]["depth"],
+                                     g["cfg"]["heads"])
+    for got, ref in ((e[:1], g["prompt"]), (e[1:], g["negative"]), (pool[:1], g["pooled"]), (pool[1:], g["negative_pooled"])):
+        assert got.shape == ref.shape and float((got - ref).abs().max()) < 1e-5

@@ -360,3 +360,39 @@ def test_dropin_lvlm_input_embeds_match_reference_golden(cuda_dev):
     # rows outside the <img_i> slots are the plain token embeddings, bit for bit
     keep = ~g["ids_cmp_mask"][0]
     assert torch.equal(got[0, keep.to(cuda_dev)].cpu(), g["emb_weight"].half()[torch.tensor(g["prompt"])][keep])
+
+
+def test_dropin_adapter_image_embeds_match_reference_golden(cuda_dev):
+    """Row a13 through the drop-in: SDXLAdapter.get_image_embeds (image_embeds branch: zero-image unconditional embeds,
+    identity discrete model, ResamplerXLV2 on the CUDA engine, chunk; the zero-image branch cached on the second call) vs
+    the reference's own method (golden adapter_image_embeds.pt)."""
+    import os
+    from src.models_ipa.adapter_modules import SDXLAdapter
+    from src.models_ipa.resampler import ResamplerXLV2
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "adapter_image_embeds.pt"), weights_only=False)
+    g["resampler_sd"] = torch.load(os.path.join(os.path.dirname(__file__), "golden", g["resampler_sd_from"]),
+                                   weights_only=False)["sd"]
+
+    class _Encoder(torch.nn.Module):       # returns what the golden's stand-in encoder returned for the zero image
+        calls = 0
+
+        def forward(self, x):
+            assert float(x.abs().max()) == 0.0 and tuple(x.shape[-2:]) == (g["image_size"], g["image_size"])
+            _Encoder.calls += 1
+            return g["zero_embeds"].half().to(x.device)
+
+    class _Identity(torch.nn.Module):
+        def encode_image_embeds(self, x):
+            return x
+
+    xl = ResamplerXLV2(**g["cfg"])
+    xl.load_state_dict(g["resampler_sd"])
+    adapter = SDXLAdapter(unet=None, resampler=xl.to(cuda_dev, torch.float16).eval())
+    adapter.visual_encoder, adapter.discrete_model, adapter.image_transform = _Encoder(), _Identity(), None
+    adapter._neg_embeds = None
+    feat = g["feat"].half().to(cuda_dev)
+    for rep in range(2):
+        pe, ne, pp, npool = adapter.get_image_embeds(image_embeds=feat, return_negative=True, image_size=g["image_size"])
+        for got, ref in ((pe, g["prompt"]), (ne, g["negative"]), (pp, g["pooled"]), (npool, g["negative_pooled"])):
+            assert got.shape == ref.shape and _rel(got, ref) < 1e-2, _rel(got, ref)
+    assert _Encoder.calls == 1, "the unconditional (zero-image) embeds are input independent: computed once"
