@@ -414,8 +414,7 @@ class LlamaEngine:
         gen = [first]
         hid_rows = []
         sched_t = torch.tensor([sched], dtype=torch.int32)
-        boi, eoi = self.img_ids_h[0], self.img_ids_h[-1]
-        n_img = len(self.img_ids_h) - 2
+        eoi = self.img_ids_h[-1]
         armed = False
         while gen[-1] != self.eos_id and len(gen) < max_new_tokens:
             # inside an image run the remaining ids are input-determined (generation.py:23-26): feed what is left of
